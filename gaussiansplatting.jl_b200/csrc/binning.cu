@@ -1,0 +1,454 @@
+// binning.cu — scan, tile-instance duplication, onesweep radix sort and per-tile ranges for sm_100a.
+//
+// Replaces, on the reference's path (src/rasterization/rasterizer.jl:333-378):
+//   cumsum!                      -> scan_kernel        single-pass decoupled look-back inclusive scan
+//   duplicate_with_keys!         -> duplicate_kernel   (utils.jl:85-120) warp-cooperative for large rects
+//   sortperm! + 2 x _permute!    -> hist_kernel + onesweep_kernel x passes   (rasterizer.jl:357-372)
+//   identify_tile_range!         -> tile_ranges_kernel (utils.jl:56-78)
+//
+// Sort: least-significant-digit radix sort, 8-bit digits, one histogram pass over the keys for all digit
+// positions, then ONE kernel per digit that ranks, looks back (chained scan over 4096-key tiles, per digit)
+// and scatters — the "onesweep" scheme.  Only the key bits that can differ are sorted: ceil(log2 T) tile bits
+// and the bits of (bits(depth) - bits(near)) (27 for near=0.2, far=1000), i.e. 40 bits -> 5 passes at
+// 1920x1088 instead of 8 for the raw 64-bit key.  LSD radix is stable, so equal keys
+// keep emission order (ascending Gaussian id), which the reference's sortperm! also guarantees.
+// The published buffers hold the canonical (tile << 32 | bits(depth)) keys and 1-based ids.
+//
+// All integer work: bit-exact by construction; compiled with default flags.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+// ----------------------------------------------------------------------------------------------------------
+// inclusive scan of tiles_touched (Int32) — decoupled look-back, 64-bit status words {flag:2 | value:62}
+// ----------------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_IPT = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;
+constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+    return *reinterpret_cast<const volatile uint32_t *>(p);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_kernel(const int64_t n, const int32_t *__restrict__ in, int32_t *__restrict__ out,
+            unsigned long long *state /* [0] = tile counter, [1..] = status */, int64_t *total) {
+    __shared__ long long s_warp[SCAN_THREADS / 32];
+    __shared__ long long s_prefix;
+    __shared__ unsigned s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = (unsigned)atomicAdd(&state[0], 1ull);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    unsigned long long *status = state + 1;
+    const int64_t base = tile * SCAN_TILE + (int64_t)tid * SCAN_IPT;
+
+    int32_t v[SCAN_IPT];
+    if (base + SCAN_IPT <= n) {
+        const int4 a = *reinterpret_cast<const int4 *>(in + base);
+        const int4 b = *reinterpret_cast<const int4 *>(in + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++) v[k] = (base + k < n) ? in[base + k] : 0;
+    }
+    long long tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) tsum += v[k];
+    // block exclusive scan of thread sums
+    long long incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    long long woff = 0, agg = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+        const long long x = s_warp[w];
+        if (w < warp) woff += x;
+        agg += x;
+    }
+    const long long texcl = woff + incl - tsum;
+
+    // look-back by warp 0
+    if (warp == 0) {
+        long long prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) atomicExch(&status[0], FLAG_INC | (unsigned long long)agg);
+        } else {
+            if (lane == 0) atomicExch(&status[tile], FLAG_AGG | (unsigned long long)agg);
+            int64_t look = tile - 1;
+            while (true) {
+                const int64_t t = look - lane;
+                unsigned long long s = FLAG_INC;  // lanes before tile 0 act as an inclusive zero
+                if (t >= 0) {
+                    do { s = ld_volatile_u64(&status[t]); } while ((s >> 62) == 0);
+                }
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+                const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;
+                long long contrib = (lane <= first_inc) ? (long long)(s & VAL_MASK) : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                prefix += contrib;
+                if (inc_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) atomicExch(&status[tile], FLAG_INC | (unsigned long long)(prefix + agg));
+        }
+        if (lane == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    long long run = s_prefix + texcl;
+    int32_t o[SCAN_IPT];
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) { run += v[k]; o[k] = (int32_t)run; }
+    if (base + SCAN_IPT <= n) {
+        *reinterpret_cast<int4 *>(out + base) = make_int4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<int4 *>(out + base + 4) = make_int4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++)
+            if (base + k < n) out[base + k] = o[k];
+    }
+    if (tile == (n - 1) / SCAN_TILE && tid == SCAN_THREADS - 1) *total = s_prefix + agg;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// duplicate_with_keys! — utils.jl:85-120
+// ----------------------------------------------------------------------------------------------------------
+constexpr int DUP_THREADS = 256;
+constexpr int DUP_SERIAL_MAX = 12;
+
+__global__ void __launch_bounds__(DUP_THREADS)
+duplicate_kernel(const int64_t n, const int32_t grid_x, const int32_t grid_y, const int32_t *__restrict__ radii,
+                 const float2 *__restrict__ means2d, const float *__restrict__ depths,
+                 const int32_t *__restrict__ offsets, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const int64_t i = (int64_t)blockIdx.x * DUP_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    uint32_t dbits = 0;
+    int64_t off = 0;
+    int cnt = 0;
+    if (i < n) {
+        const int32_t r = radii[i];
+        if (r > 0) {
+            const float2 m = means2d[i];
+            get_rect(m.x, m.y, r, grid_x, grid_y, x0, y0, x1, y1);
+            dbits = __float_as_uint(depths[i]);
+            off = (i == 0) ? 0 : (int64_t)offsets[i - 1];
+            cnt = (x1 - x0) * (y1 - y0);
+        }
+    }
+    const uint32_t id = (uint32_t)(i + 1);  // 1-based, as the reference emits
+    if (cnt > 0 && cnt <= DUP_SERIAL_MAX) {
+        int64_t o = off;
+        for (int32_t y = y0; y < y1; y++)
+            for (int32_t x = x0; x < x1; x++) {
+                keys[o] = ((uint64_t)((uint64_t)y * (uint64_t)grid_x + (uint64_t)x) << 32) | dbits;
+                vals[o] = id;
+                o++;
+            }
+    }
+    // large rects: the whole warp emits one Gaussian's tiles (the reference's serial loop is the load-imbalance
+    // hot spot for big splats)
+    unsigned big = __ballot_sync(0xffffffffu, cnt > DUP_SERIAL_MAX);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+        const int32_t bx1 = __shfl_sync(0xffffffffu, x1, src);
+        const int bcnt = __shfl_sync(0xffffffffu, cnt, src);
+        const uint32_t bd = __shfl_sync(0xffffffffu, dbits, src), bid = __shfl_sync(0xffffffffu, id, src);
+        const int64_t boff = __shfl_sync(0xffffffffu, off, src);
+        const int w = bx1 - bx0;
+        for (int t = lane; t < bcnt; t += 32) {
+            const int ty = by0 + t / w, tx = bx0 + t % w;
+            keys[boff + t] = ((uint64_t)((uint64_t)ty * (uint64_t)grid_x + (uint64_t)tx) << 32) | bd;
+            vals[boff + t] = bid;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// onesweep radix sort on the compact key  ck = (tile << depth_bits) | (bits(depth) - depth_base)
+// ----------------------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_IPT = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 keys per CTA
+constexpr int SORT_MAX_PASSES = 8;
+constexpr uint32_t ST_AGG = 1u << 30, ST_INC = 2u << 30, ST_MASK = (1u << 30) - 1;
+
+__device__ __forceinline__ uint64_t compact_key(uint64_t key, int depth_bits, uint32_t depth_base) {
+    const uint32_t lo = (uint32_t)key - depth_base;
+    return ((key >> 32) << depth_bits) | (uint64_t)lo;
+}
+
+__global__ void __launch_bounds__(256)
+hist_kernel(const uint64_t *__restrict__ keys, const int64_t m, const int depth_bits, const uint32_t depth_base,
+            const int passes, uint32_t *__restrict__ ghist /* [passes][256] */) {
+    __shared__ uint32_t sh[SORT_MAX_PASSES * 256];
+    const int lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < passes * 256; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t m_round = ((m + 31) / 32) * 32;  // keep warps converged for match_any
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m_round; i += stride) {
+        const bool valid = i < m;
+        const uint64_t ck = valid ? compact_key(keys[i], depth_bits, depth_base) : 0;
+        for (int p = 0; p < passes; p++) {
+            const uint32_t d = valid ? (uint32_t)((ck >> (8 * p)) & 255u) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);  // warp-aggregated: tile digits cluster
+            if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p * 256 + d], (uint32_t)__popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < passes * 256; k += blockDim.x)
+        if (sh[k]) atomicAdd(&ghist[k], sh[k]);
+}
+
+struct SortSmem {
+    uint64_t keys[SORT_TILE];
+    uint32_t vals[SORT_TILE];
+    uint32_t whist[SORT_WARPS][256];
+    uint32_t excl[256];
+    uint32_t gbase[256];
+    uint32_t wsum[SORT_WARPS];
+    uint32_t wsum2[SORT_WARPS];
+    uint32_t tile;
+};
+
+__global__ void __launch_bounds__(SORT_THREADS)
+onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, const int64_t m, const int shift,
+                const int depth_bits, const uint32_t depth_base, const uint32_t *__restrict__ ghist /* [256] */,
+                uint32_t *status /* [tiles][256] */, uint32_t *tile_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortSmem &S = *reinterpret_cast<SortSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) S.tile = atomicAdd(tile_counter, 1u);
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) S.whist[w][tid] = 0;
+    __syncthreads();
+    const int64_t tile = S.tile;
+    const int64_t tile_base = tile * SORT_TILE;
+    const int cnt = (int)((m - tile_base) < SORT_TILE ? (m - tile_base) : SORT_TILE);
+
+    // ---- load (warp-striped inside each warp's contiguous 512-key chunk) and rank by digit ----------------
+    uint64_t key[SORT_IPT];
+    uint32_t val[SORT_IPT];
+    uint16_t rnk[SORT_IPT];
+    uint32_t *whist = S.whist[warp];
+    const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < SORT_IPT; j++) {
+        const int local = warp * (32 * SORT_IPT) + j * 32 + lane;
+        const bool valid = local < cnt;
+        key[j] = valid ? keys_in[tile_base + local] : ~0ull;
+        val[j] = valid ? vals_in[tile_base + local] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < SORT_IPT; j++) {
+        const int local = warp * (32 * SORT_IPT) + j * 32 + lane;
+        const bool valid = local < cnt;
+        const uint32_t d = valid ? (uint32_t)((compact_key(key[j], depth_bits, depth_base) >> shift) & 255u) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t pre = 0;
+        if (valid && lane == leader) {
+            pre = whist[d];
+            whist[d] = pre + (uint32_t)__popc(peers);
+        }
+        pre = __shfl_sync(0xffffffffu, pre, leader);
+        rnk[j] = (uint16_t)(pre + (uint32_t)__popc(peers & lt_mask));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per-digit: exclusive over warps, CTA count, chained look-back over tiles --------------------------
+    uint32_t count = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) {
+        const uint32_t c = S.whist[w][tid];
+        S.whist[w][tid] = count;
+        count += c;
+    }
+    uint32_t *my_status = status + tile * 256 + tid;
+    uint32_t tiles_prefix = 0;
+    if (tile == 0) {
+        atomicExch(my_status, ST_INC | count);
+    } else {
+        atomicExch(my_status, ST_AGG | count);
+        for (int64_t t = tile - 1; t >= 0; --t) {
+            uint32_t s;
+            do { s = ld_volatile_u32(status + t * 256 + tid); } while ((s >> 30) == 0);
+            tiles_prefix += s & ST_MASK;
+            if ((s >> 30) == 2) break;
+        }
+        atomicExch(my_status, ST_INC | (tiles_prefix + count));
+    }
+    // two CTA-wide exclusive scans over the 256 digits: this tile's counts and the global histogram
+    const uint32_t gh = ghist[tid];
+    uint32_t inc1 = count, inc2 = gh;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y1 = __shfl_up_sync(0xffffffffu, inc1, o), y2 = __shfl_up_sync(0xffffffffu, inc2, o);
+        if (lane >= o) { inc1 += y1; inc2 += y2; }
+    }
+    if (lane == 31) { S.wsum[warp] = inc1; S.wsum2[warp] = inc2; }
+    __syncthreads();
+    uint32_t off1 = 0, off2 = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++)
+        if (w < warp) { off1 += S.wsum[w]; off2 += S.wsum2[w]; }
+    const uint32_t excl = off1 + inc1 - count;
+    const uint32_t gexcl = off2 + inc2 - gh;
+    S.excl[tid] = excl;
+    S.gbase[tid] = gexcl + tiles_prefix - excl;  // global position = gbase[d] + local sorted position
+    __syncthreads();
+
+    // ---- scatter into shared memory in digit order, then stream out runs ----------------------------------
+#pragma unroll
+    for (int j = 0; j < SORT_IPT; j++) {
+        const int local = warp * (32 * SORT_IPT) + j * 32 + lane;
+        if (local < cnt) {
+            const uint32_t d = (uint32_t)((compact_key(key[j], depth_bits, depth_base) >> shift) & 255u);
+            const uint32_t pos = S.excl[d] + whist[d] + rnk[j];
+            S.keys[pos] = key[j];
+            S.vals[pos] = val[j];
+        }
+    }
+    __syncthreads();
+    for (int p = tid; p < cnt; p += SORT_THREADS) {
+        const uint64_t k = S.keys[p];
+        const uint32_t d = (uint32_t)((compact_key(k, depth_bits, depth_base) >> shift) & 255u);
+        const uint32_t gp = S.gbase[d] + (uint32_t)p;
+        keys_out[gp] = k;
+        vals_out[gp] = S.vals[p];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// identify_tile_range! — utils.jl:56-78   (ranges pre-zeroed by the caller, rasterizer.jl:375)
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tile_ranges_kernel(const int64_t m, const uint64_t *__restrict__ keys, uint32_t *__restrict__ ranges) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t tile = (uint32_t)(keys[i] >> 32);
+    if (i == 0) {
+        ranges[2 * (int64_t)tile] = 0u;
+    } else {
+        const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+        if (tile != prev) {
+            ranges[2 * (int64_t)prev + 1] = (uint32_t)i;
+            ranges[2 * (int64_t)tile] = (uint32_t)i;
+        }
+    }
+    if (i == m - 1) ranges[2 * (int64_t)tile + 1] = (uint32_t)m;
+}
+
+int bit_length(uint64_t x) {
+    int b = 0;
+    while (x) { b++; x >>= 1; }
+    return b;
+}
+
+}  // namespace
+
+// ---- host side ---------------------------------------------------------------------------------------------
+size_t scan_state_words(int64_t n) {  // in 64-bit words
+    return 1 + (size_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+}
+
+void launch_scan_tiles(int64_t n, const int32_t *tiles_touched, int32_t *points_offset, uint32_t *scan_state,
+                       int64_t *total_dev, cudaStream_t s) {
+    if (n <= 0) return;
+    const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    cudaMemsetAsync(scan_state, 0, scan_state_words(n) * sizeof(unsigned long long), s);
+    scan_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(n, tiles_touched, points_offset,
+                                                        reinterpret_cast<unsigned long long *>(scan_state), total_dev);
+    count_launch();
+}
+
+void launch_duplicate(const DevCamera &cam, int64_t n, const GeomPtrs &g, uint64_t *keys, uint32_t *vals,
+                      cudaStream_t s) {
+    if (n <= 0) return;
+    const int64_t blocks = (n + DUP_THREADS - 1) / DUP_THREADS;
+    duplicate_kernel<<<(unsigned)blocks, DUP_THREADS, 0, s>>>(n, cam.grid_x, cam.grid_y, g.radii, g.means2d, g.depths,
+                                                             g.points_offset, keys, vals);
+    count_launch();
+}
+
+SortPlan make_sort_plan(int64_t n_tiles, float near_plane, float far_plane) {
+    SortPlan p;
+    p.tile_bits = bit_length((uint64_t)(n_tiles > 1 ? n_tiles - 1 : 1));
+    uint32_t nb, fb;
+    memcpy(&nb, &near_plane, 4);
+    memcpy(&fb, &far_plane, 4);
+    if (near_plane > 0.f && far_plane > near_plane) {  // depths in (near, far): bits monotone, sign bit clear
+        p.depth_base = nb;
+        p.depth_bits = bit_length((uint64_t)(fb - nb));
+    } else {  // degenerate planes: keep the raw 32 depth bits, exactly the reference's ordering
+        p.depth_base = 0;
+        p.depth_bits = 32;
+    }
+    if (p.depth_bits < 1) p.depth_bits = 1;
+    p.passes = (p.tile_bits + p.depth_bits + 7) / 8;
+    return p;
+}
+
+size_t sort_temp_words(int64_t m, const SortPlan &plan) {  // in 32-bit words
+    const size_t tiles = (size_t)((m + SORT_TILE - 1) / SORT_TILE);
+    return (size_t)plan.passes * 256 /* ghist */ + (size_t)plan.passes * tiles * 256 /* status */ +
+           SORT_MAX_PASSES /* tile counters */;
+}
+
+void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in, const uint32_t *vals_in,
+                       uint64_t *keys_out, uint32_t *vals_out, uint64_t *keys_tmp, uint32_t *vals_tmp,
+                       uint32_t *temp_words, cudaStream_t s) {
+    if (m <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+        attr_set = true;
+    }
+    const size_t tiles = (size_t)((m + SORT_TILE - 1) / SORT_TILE);
+    cudaMemsetAsync(temp_words, 0, sort_temp_words(m, plan) * sizeof(uint32_t), s);
+    uint32_t *ghist = temp_words;
+    uint32_t *status = ghist + (size_t)plan.passes * 256;
+    uint32_t *counters = status + (size_t)plan.passes * tiles * 256;
+    int hb = (int)((m + 256 * 16 - 1) / (256 * 16));
+    if (hb > 148 * 8) hb = 148 * 8;
+    hist_kernel<<<hb, 256, 0, s>>>(keys_in, m, plan.depth_bits, plan.depth_base, plan.passes, ghist);
+    count_launch();
+    const uint64_t *ksrc = keys_in;
+    const uint32_t *vsrc = vals_in;
+    for (int p = 0; p < plan.passes; p++) {
+        // the chain must end in (keys_out, vals_out) and never write the input
+        const bool to_out = ((plan.passes - 1 - p) % 2) == 0;
+        uint64_t *kdst = to_out ? keys_out : keys_tmp;
+        uint32_t *vdst = to_out ? vals_out : vals_tmp;
+        onesweep_kernel<<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem), s>>>(
+            ksrc, vsrc, kdst, vdst, m, 8 * p, plan.depth_bits, plan.depth_base, ghist + (size_t)p * 256,
+            status + (size_t)p * tiles * 256, counters + p);
+        count_launch();
+        ksrc = kdst;
+        vsrc = vdst;
+    }
+}
+
+void launch_tile_ranges(int64_t m, const uint64_t *keys_sorted, uint32_t *ranges, cudaStream_t s) {
+    if (m <= 0) return;
+    tile_ranges_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(m, keys_sorted, ranges);
+    count_launch();
+}

@@ -1,0 +1,106 @@
+// common.cuh — shared declarations of libgsrast (sm_100a).  Internal; the public surface is include/gsrast.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gsrast.h"
+
+#define GSR_TILE 16          // BLOCK = (16,16)            GaussianSplatting.jl:55-56
+#define GSR_TILE_PIXELS 256  // BLOCK_SIZE                 GaussianSplatting.jl:57
+
+// Kernel-side camera + config (by value in the parameter space; R/t optionally re-read from device memory).
+struct DevCamera {
+    float R[9];  // column-major w2c rotation
+    float t[3];
+    float focal[2];
+    float principal[2];
+    float cam_center[3];
+    const float *R_dev;
+    const float *t_dev;
+    int32_t width, height;
+    int32_t grid_x, grid_y;
+    float near_plane, far_plane, blur_eps;
+    int32_t radius_clip;
+};
+
+// Per-Gaussian packed record streamed by the compositing kernels (written by preprocess):
+//   float4 q0 = {mean2d.x, mean2d.y, conic.a, conic.b}
+//   float4 q1 = {conic.c, opacity, f0, f1}
+//   float4 q2 = {f2, f3, f4, f5}            (channels <= 6 -> 3 quads, 48 B)
+//   float4 q3 = {f6, f7, 0, 0}              (channels == 8 -> 4 quads, 64 B)
+__host__ __device__ constexpr int rec_quads(int channels) { return channels <= 6 ? 3 : 4; }
+// Per-Gaussian gradient accumulator filled by the backward compositing kernel (same quad count):
+//   {v_mean2d.x, v_mean2d.y, v_conic.a, v_conic.b, v_conic.c, v_opacity, v_f0 ... v_f(C-1), pad}
+__host__ __device__ constexpr int acc_floats(int channels) { return 4 * rec_quads(channels); }
+
+struct GeomPtrs {  // GeometryState (states.jl:2-47), SoA
+    float *depths;
+    float2 *means2d;
+    float2 *grad_means2d;
+    float *rgbs;            // [n,3]
+    uint8_t *clamped;       // [n,3]
+    int32_t *tiles_touched;
+    int32_t *points_offset;
+    float *conics;          // [n,3]
+    int32_t *radii;
+    float *normals;         // [n,3] or null
+    float4 *rec;            // [n, rec_quads]
+    float *gacc;            // [n, acc_floats]
+};
+
+// ---- launchers (one per translation unit) ---------------------------------------------------------------
+void launch_preprocess(const DevCamera &cam, int64_t n, int sh_degree, int K, int channels, const float *means,
+                       const float *shs, const float *opac, const float *scales, const float *rots,
+                       const GeomPtrs &g, cudaStream_t s);
+
+void launch_scan_tiles(int64_t n, const int32_t *tiles_touched, int32_t *points_offset, uint32_t *scan_state,
+                       int64_t *total_dev, cudaStream_t s);
+size_t scan_state_words(int64_t n);
+
+void launch_duplicate(const DevCamera &cam, int64_t n, const GeomPtrs &g, uint64_t *keys, uint32_t *vals,
+                      cudaStream_t s);
+
+struct SortPlan {
+    int tile_bits, depth_bits, passes;
+    uint32_t depth_base;
+};
+SortPlan make_sort_plan(int64_t n_tiles, float near_plane, float far_plane);
+size_t sort_temp_words(int64_t m, const SortPlan &plan);
+// keys_in/vals_in are left intact; result lands in keys_out/vals_out; (keys_tmp, vals_tmp) is scratch of size m.
+void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in, const uint32_t *vals_in,
+                       uint64_t *keys_out, uint32_t *vals_out, uint64_t *keys_tmp, uint32_t *vals_tmp,
+                       uint32_t *temp_words, cudaStream_t s);
+
+void launch_tile_ranges(int64_t m, const uint64_t *keys_sorted, uint32_t *ranges, cudaStream_t s);
+
+void launch_render_forward(int channels, int math_mode, int width, int height, const uint32_t *ranges,
+                           const uint32_t *vals_sorted, const float4 *rec, const float *bg, float *image,
+                           uint32_t *n_contrib, float *accum_alpha, uint8_t *covis, float *uncert, cudaStream_t s);
+
+void launch_render_backward(int channels, int math_mode, int width, int height, const uint32_t *ranges,
+                            const uint32_t *vals_sorted, const float4 *rec, const float *bg, const float *vpixels,
+                            const uint32_t *n_contrib, const float *accum_alpha, float *gacc, cudaStream_t s);
+
+void launch_backward_gaussians(const DevCamera &cam, int64_t n, int sh_degree, int K, int channels,
+                               const float *means, const float *shs, const float *scales, const float *rots,
+                               const GeomPtrs &g, float *vmeans, float *vshs, float *vopac, float *vscales,
+                               float *vrot, float *vR, float *vt, int accumulate, cudaStream_t s);
+
+void launch_update_stats(int64_t n, const int32_t *radii, const float2 *grad_means2d, uint32_t width,
+                         uint32_t height, int32_t *max_radii, float *accum, float *denom, cudaStream_t s);
+
+int launch_fp32_peak(cudaStream_t s, double *ms, double *flops);
+
+void count_launch(int n = 1);
+
+// get_rect — utils.jl:18-29, fp32 op order preserved (callers compile with -fmad=false or use no FMA-able form).
+__device__ __forceinline__ void get_rect(float px, float py, int32_t radius, int32_t gx, int32_t gy, int32_t &x0,
+                                         int32_t &y0, int32_t &x1, int32_t &y1) {
+    const float r = (float)radius;
+    // (p - r) / 16 ; floor ; trunc ; clamp.  Division by 16 is exact scaling, written as the reference does.
+    x0 = min(max(__float2int_rz(floorf(__fdiv_rn(__fsub_rn(px, r), 16.0f))), 0), gx);
+    y0 = min(max(__float2int_rz(floorf(__fdiv_rn(__fsub_rn(py, r), 16.0f))), 0), gy);
+    // gpu_cld(p + r, 16) = trunc(floor(((p + r) + 16 - 1) / 16))
+    x1 = min(max(__float2int_rz(floorf(__fdiv_rn(__fsub_rn(__fadd_rn(__fadd_rn(px, r), 16.0f), 1.0f), 16.0f))), 0), gx);
+    y1 = min(max(__float2int_rz(floorf(__fdiv_rn(__fsub_rn(__fadd_rn(__fadd_rn(py, r), 16.0f), 1.0f), 16.0f))), 0), gy);
+}

@@ -1,0 +1,557 @@
+// gsrast.cu — C ABI (include/gsrast.h), handle / workspace lifecycle and stage orchestration.
+//
+// Mirrors the control flow of `rasterize` (src/rasterization/rasterizer.jl:255-408) and `∇rasterize`
+// (:416-550): the handle plays the role of `rast.{g,b,i}state` (states.jl), grown monotonically like
+// rasterizer.jl:275-278,340-343 and released by gsr_release_scene_buffers (rasterizer.jl:111-123).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct GsrHandle {
+    GsrConfig cfg;
+    int grid_x = 0, grid_y = 0;
+    int64_t n_tiles = 0;
+    SortPlan plan;
+    std::string err;
+    size_t bytes = 0;  // device bytes owned
+
+    // GeometryState
+    int64_t cap_n = 0;
+    GeomPtrs g{};
+    // BinningState
+    int64_t cap_m = 0;
+    uint64_t *keys_unsorted = nullptr, *keys_sorted = nullptr, *keys_tmp = nullptr;
+    uint32_t *vals_unsorted = nullptr, *vals_sorted = nullptr, *vals_tmp = nullptr;
+    uint32_t *sort_temp = nullptr;
+    size_t sort_temp_cap = 0;  // words
+    // ImageState
+    uint32_t *ranges = nullptr, *n_contrib = nullptr;
+    float *accum_alpha = nullptr;
+    // scan
+    uint32_t *scan_state = nullptr;
+    size_t scan_cap = 0;  // 64-bit words
+    int64_t *total_dev = nullptr;
+    int64_t *total_host = nullptr;  // pinned
+
+    // state of the last forward
+    int64_t last_n = 0, last_m = 0;
+    bool fwd_valid = false;
+
+    // per-stage timing
+    bool profile = false;
+    cudaEvent_t ev[2 * GSR_NUM_STAGES] = {};
+    bool ev_used[GSR_NUM_STAGES] = {};
+
+    // staging for the host-buffer entry point
+    DevBuf st_means, st_shs, st_opac, st_scales, st_rots, st_vpix, st_image, st_vmeans, st_vshs, st_vopac, st_vscales,
+        st_vrot;
+};
+
+namespace {
+
+int fail(GsrHandle *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(GsrHandle *h, cudaError_t e, const char *what) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    return fail(h, e == cudaErrorMemoryAllocation ? GSR_ENOMEM : GSR_ECUDA, buf);
+}
+#define CK(call)                                                    \
+    do {                                                            \
+        cudaError_t e_ = (call);                                    \
+        if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);      \
+    } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(GsrHandle *h, T **p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T));
+    if (e == cudaSuccess) h->bytes += count * sizeof(T);
+    return e;
+}
+template <typename T>
+void dev_free(GsrHandle *h, T *&p, size_t count) {
+    if (p) {
+        cudaFree(p);
+        h->bytes -= count * sizeof(T);
+        p = nullptr;
+    }
+}
+
+void free_geometry(GsrHandle *h) {
+    const size_t n = (size_t)h->cap_n;
+    const int ch = h->cfg.channels;
+    dev_free(h, h->g.depths, n);
+    dev_free(h, h->g.means2d, n);
+    dev_free(h, h->g.grad_means2d, n);
+    dev_free(h, h->g.rgbs, 3 * n);
+    dev_free(h, h->g.clamped, 3 * n);
+    dev_free(h, h->g.tiles_touched, n);
+    dev_free(h, h->g.points_offset, n);
+    dev_free(h, h->g.conics, 3 * n);
+    dev_free(h, h->g.radii, n);
+    if (ch > 5) dev_free(h, h->g.normals, 3 * n);
+    dev_free(h, h->g.rec, (size_t)rec_quads(ch) * n);
+    dev_free(h, h->g.gacc, (size_t)acc_floats(ch) * n);
+    dev_free(h, h->scan_state, 2 * h->scan_cap);
+    h->scan_cap = 0;
+    h->cap_n = 0;
+}
+
+int ensure_geometry(GsrHandle *h, int64_t n) {
+    if (n <= h->cap_n) return GSR_OK;
+    free_geometry(h);  // rasterizer.jl:275-278: a larger scene replaces the whole GeometryState
+    const size_t c = (size_t)n;
+    const int ch = h->cfg.channels;
+    CK(dev_alloc(h, &h->g.depths, c));
+    CK(dev_alloc(h, &h->g.means2d, c));
+    CK(dev_alloc(h, &h->g.grad_means2d, c));
+    CK(dev_alloc(h, &h->g.rgbs, 3 * c));
+    CK(dev_alloc(h, &h->g.clamped, 3 * c));
+    CK(dev_alloc(h, &h->g.tiles_touched, c));
+    CK(dev_alloc(h, &h->g.points_offset, c));
+    CK(dev_alloc(h, &h->g.conics, 3 * c));
+    CK(dev_alloc(h, &h->g.radii, c));
+    if (ch > 5) CK(dev_alloc(h, &h->g.normals, 3 * c));
+    CK(dev_alloc(h, &h->g.rec, (size_t)rec_quads(ch) * c));
+    CK(dev_alloc(h, &h->g.gacc, (size_t)acc_floats(ch) * c));
+    h->scan_cap = scan_state_words(n);
+    CK(dev_alloc(h, &h->scan_state, 2 * h->scan_cap));
+    h->cap_n = n;
+    // KA.zeros in the reference (states.jl:30-47): stale-state reads of never-visible rows see zeros
+    CK(cudaMemset(h->g.depths, 0, c * 4));
+    CK(cudaMemset(h->g.means2d, 0, c * 8));
+    CK(cudaMemset(h->g.grad_means2d, 0, c * 8));
+    CK(cudaMemset(h->g.rgbs, 0, c * 12));
+    CK(cudaMemset(h->g.clamped, 0, c * 3));
+    CK(cudaMemset(h->g.conics, 0, c * 12));
+    CK(cudaMemset(h->g.radii, 0, c * 4));
+    if (ch > 5) CK(cudaMemset(h->g.normals, 0, c * 12));
+    return GSR_OK;
+}
+
+void free_binning(GsrHandle *h) {
+    const size_t m = (size_t)h->cap_m;
+    dev_free(h, h->keys_unsorted, m);
+    dev_free(h, h->keys_sorted, m);
+    dev_free(h, h->keys_tmp, m);
+    dev_free(h, h->vals_unsorted, m);
+    dev_free(h, h->vals_sorted, m);
+    dev_free(h, h->vals_tmp, m);
+    dev_free(h, h->sort_temp, h->sort_temp_cap);
+    h->sort_temp_cap = 0;
+    h->cap_m = 0;
+}
+
+int ensure_binning(GsrHandle *h, int64_t m) {
+    if (m <= h->cap_m) return GSR_OK;
+    free_binning(h);  // rasterizer.jl:340-343
+    const int64_t cap = m + m / 4 + 1024;  // slack: M drifts upward during training
+    const size_t c = (size_t)cap;
+    CK(dev_alloc(h, &h->keys_unsorted, c));
+    CK(dev_alloc(h, &h->keys_sorted, c));
+    CK(dev_alloc(h, &h->keys_tmp, c));
+    CK(dev_alloc(h, &h->vals_unsorted, c));
+    CK(dev_alloc(h, &h->vals_sorted, c));
+    CK(dev_alloc(h, &h->vals_tmp, c));
+    h->sort_temp_cap = sort_temp_words(cap, h->plan);
+    CK(dev_alloc(h, &h->sort_temp, h->sort_temp_cap));
+    h->cap_m = cap;
+    return GSR_OK;
+}
+
+void make_dev_camera(const GsrHandle *h, const GsrCamera *cam, DevCamera *d) {
+    memcpy(d->R, cam->R, sizeof d->R);
+    memcpy(d->t, cam->t, sizeof d->t);
+    memcpy(d->focal, cam->focal, sizeof d->focal);
+    memcpy(d->principal, cam->principal, sizeof d->principal);
+    memcpy(d->cam_center, cam->cam_center, sizeof d->cam_center);
+    d->R_dev = (cam->R_dev && cam->t_dev) ? cam->R_dev : nullptr;
+    d->t_dev = (cam->R_dev && cam->t_dev) ? cam->t_dev : nullptr;
+    d->width = h->cfg.width;
+    d->height = h->cfg.height;
+    d->grid_x = h->grid_x;
+    d->grid_y = h->grid_y;
+    d->near_plane = h->cfg.near_plane;
+    d->far_plane = h->cfg.far_plane;
+    d->blur_eps = h->cfg.blur_eps;
+    d->radius_clip = h->cfg.radius_clip;
+}
+
+struct StageTimer {  // records an event pair around a stage when profiling is on
+    GsrHandle *h;
+    cudaStream_t s;
+    int stage;
+    StageTimer(GsrHandle *h_, cudaStream_t s_, int stage_) : h(h_), s(s_), stage(stage_) {
+        if (h->profile) cudaEventRecord(h->ev[2 * stage], s);
+    }
+    ~StageTimer() {
+        if (h->profile) {
+            cudaEventRecord(h->ev[2 * stage + 1], s);
+            h->ev_used[stage] = true;
+        }
+    }
+};
+
+int ensure_stage(GsrHandle *h, DevBuf &b, size_t bytes) {
+    if (bytes <= b.bytes) return GSR_OK;
+    if (b.p) { cudaFree(b.p); h->bytes -= b.bytes; b.p = nullptr; b.bytes = 0; }
+    CK(cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    h->bytes += bytes;
+    return GSR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *gsr_version(void) { return "gsrast 0.1.0 (sm_100a)"; }
+
+const char *gsr_last_error(const GsrHandle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t gsr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int gsr_create(const GsrConfig *cfg, GsrHandle **out) {
+    GsrHandle *h = nullptr;
+    if (!cfg || !out) return fail(h, GSR_EINVAL, "gsr_create: null argument");
+    *out = nullptr;
+    if (cfg->width <= 0 || cfg->height <= 0 || cfg->width % 16 != 0 || cfg->height % 16 != 0)
+        return fail(h, GSR_EINVAL, "width and height must be positive multiples of 16 (rasterizer.jl:66)");
+    if (cfg->channels != 3 && cfg->channels != 5 && cfg->channels != 8)
+        return fail(h, GSR_EINVAL, "Invalid render mode: channels must be 3 (:rgb), 5 (:rgbd) or 8 (:rgbdn)");
+    if (cfg->math_mode != GSR_MATH_REFERENCE && cfg->math_mode != GSR_MATH_FAST)
+        return fail(h, GSR_EINVAL, "math_mode must be GSR_MATH_REFERENCE or GSR_MATH_FAST");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(h, GSR_ECUDA, "no CUDA device available: libgsrast has no CPU fallback");
+    }
+    h = new GsrHandle();
+    h->cfg = *cfg;
+    h->grid_x = cfg->width / GSR_TILE;
+    h->grid_y = cfg->height / GSR_TILE;
+    h->n_tiles = (int64_t)h->grid_x * h->grid_y;
+    h->plan = make_sort_plan(h->n_tiles, cfg->near_plane, cfg->far_plane);
+    const size_t px = (size_t)cfg->width * cfg->height;
+    int rc = GSR_OK;
+    do {
+        if ((e = dev_alloc(h, &h->ranges, 2 * (size_t)h->n_tiles)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->n_contrib, px)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->accum_alpha, px)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->total_dev, 1)) != cudaSuccess) break;
+        if ((e = cudaMallocHost(reinterpret_cast<void **>(&h->total_host), sizeof(int64_t))) != cudaSuccess) break;
+        if ((e = cudaMemset(h->ranges, 0, 2 * (size_t)h->n_tiles * 4)) != cudaSuccess) break;
+        if ((e = cudaMemset(h->n_contrib, 0, px * 4)) != cudaSuccess) break;
+        if ((e = cudaMemset(h->accum_alpha, 0, px * 4)) != cudaSuccess) break;
+    } while (0);
+    if (e != cudaSuccess) {
+        rc = cuda_fail(nullptr, e, "gsr_create allocation");
+        gsr_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return GSR_OK;
+}
+
+int gsr_release_scene_buffers(GsrHandle *h) {
+    if (!h) return GSR_EINVAL;
+    free_geometry(h);
+    free_binning(h);
+    DevBuf *st[] = {&h->st_means, &h->st_shs, &h->st_opac, &h->st_scales, &h->st_rots, &h->st_vpix,
+                    &h->st_image, &h->st_vmeans, &h->st_vshs, &h->st_vopac, &h->st_vscales, &h->st_vrot};
+    for (DevBuf *b : st)
+        if (b->p) { cudaFree(b->p); h->bytes -= b->bytes; b->p = nullptr; b->bytes = 0; }
+    h->fwd_valid = false;
+    h->last_n = h->last_m = 0;
+    return GSR_OK;
+}
+
+int gsr_destroy(GsrHandle *h) {
+    if (!h) return GSR_OK;
+    gsr_release_scene_buffers(h);
+    const size_t px = (size_t)h->cfg.width * h->cfg.height;
+    dev_free(h, h->ranges, 2 * (size_t)h->n_tiles);
+    dev_free(h, h->n_contrib, px);
+    dev_free(h, h->accum_alpha, px);
+    dev_free(h, h->total_dev, 1);
+    if (h->total_host) cudaFreeHost(h->total_host);
+    for (cudaEvent_t e : h->ev)
+        if (e) cudaEventDestroy(e);
+    delete h;
+    return GSR_OK;
+}
+
+int gsr_memory_usage(const GsrHandle *h, size_t *bytes) {
+    if (!h || !bytes) return GSR_EINVAL;
+    *bytes = h->bytes;
+    return GSR_OK;
+}
+
+int gsr_get_state(const GsrHandle *h, GsrStateViews *v) {
+    if (!h || !v) return GSR_EINVAL;
+    memset(v, 0, sizeof *v);
+    v->n = h->last_n;
+    v->n_rendered = h->last_m;
+    v->radii = h->g.radii;
+    v->grad_means2d = reinterpret_cast<float *>(h->g.grad_means2d);
+    v->means2d = reinterpret_cast<const float *>(h->g.means2d);
+    v->depths = h->g.depths;
+    v->conics = h->g.conics;
+    v->rgbs = h->g.rgbs;
+    v->clamped = h->g.clamped;
+    v->tiles_touched = h->g.tiles_touched;
+    v->points_offset = h->g.points_offset;
+    v->normals = h->g.normals;
+    v->keys_unsorted = h->keys_unsorted;
+    v->values_unsorted = h->vals_unsorted;
+    v->keys_sorted = h->keys_sorted;
+    v->values_sorted = h->vals_sorted;
+    v->ranges = h->ranges;
+    v->n_contrib = h->n_contrib;
+    v->accum_alpha = h->accum_alpha;
+    return GSR_OK;
+}
+
+int gsr_forward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K, const float *means,
+                const float *shs, const float *opacities, const float *scales, const float *rotations,
+                const float background[3], float *image_out, uint8_t *covis, float *uncert, int64_t *n_rendered,
+                void *stream) {
+    if (!h) return GSR_EINVAL;
+    if (!cam || !image_out || !background) return fail(h, GSR_EINVAL, "gsr_forward: null argument");
+    if (n < 0 || sh_degree < 0 || sh_degree > 3 || K < (sh_degree + 1) * (sh_degree + 1))
+        return fail(h, GSR_EINVAL, "gsr_forward: need 0 <= sh_degree <= 3 and K >= (sh_degree+1)^2");
+    if (n > 0 && (!means || !shs || !opacities || !scales || !rotations))
+        return fail(h, GSR_EINVAL, "gsr_forward: null parameter array");
+    if (reinterpret_cast<uintptr_t>(rotations) & 15)
+        return fail(h, GSR_EINVAL, "gsr_forward: rotations must be 16-byte aligned (128-bit loads, projection.jl:85)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int ch = h->cfg.channels;
+    const size_t image_bytes = (size_t)ch * h->cfg.width * h->cfg.height * sizeof(float);
+    h->fwd_valid = false;
+    if (n_rendered) *n_rendered = 0;
+
+    int rc = ensure_geometry(h, n);
+    if (rc) return rc;
+    DevCamera dc;
+    make_dev_camera(h, cam, &dc);
+
+    int64_t m = 0;
+    if (h->profile)
+        for (int k = 0; k < GSR_NUM_STAGES; k++) h->ev_used[k] = false;
+    if (n > 0) {
+        {
+            StageTimer tm(h, s, GSR_STAGE_PREPROCESS);
+            launch_preprocess(dc, n, sh_degree, K, ch, means, shs, opacities, scales, rotations, h->g, s);
+        }
+        {
+            StageTimer tm(h, s, GSR_STAGE_SCAN);
+            launch_scan_tiles(n, h->g.tiles_touched, h->g.points_offset, h->scan_state, h->total_dev, s);
+            CK(cudaMemcpyAsync(h->total_host, h->total_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaStreamSynchronize(s));  // the one host sync of the forward (rasterizer.jl:337)
+        m = *h->total_host;
+    }
+    h->last_n = n;
+    h->last_m = m;
+    if (m == 0) {  // rasterizer.jl:283,338: zero image, NOT background
+        CK(cudaMemsetAsync(image_out, 0, image_bytes, s));
+        h->fwd_valid = true;
+        return GSR_OK;
+    }
+    if (m >= (1ll << 30)) return fail(h, GSR_EINVAL, "gsr_forward: more than 2^30 tile instances");
+    rc = ensure_binning(h, m);
+    if (rc) return rc;
+
+    {
+        StageTimer tm(h, s, GSR_STAGE_DUPLICATE);
+        launch_duplicate(dc, n, h->g, h->keys_unsorted, h->vals_unsorted, s);
+    }
+    {
+        StageTimer tm(h, s, GSR_STAGE_SORT);
+        launch_sort_pairs(h->plan, m, h->keys_unsorted, h->vals_unsorted, h->keys_sorted, h->vals_sorted, h->keys_tmp,
+                          h->vals_tmp, h->sort_temp, s);
+    }
+    {
+        StageTimer tm(h, s, GSR_STAGE_RANGES);
+        CK(cudaMemsetAsync(h->ranges, 0, 2 * (size_t)h->n_tiles * sizeof(uint32_t), s));  // rasterizer.jl:375
+        launch_tile_ranges(m, h->keys_sorted, h->ranges, s);
+    }
+    {
+        StageTimer tm(h, s, GSR_STAGE_RENDER_FWD);
+        float bg[8] = {background[0], background[1], background[2], 0.f, 0.f, 0.f, 0.f, 0.f};  // rasterizer.jl:411-414
+        launch_render_forward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,
+                              bg, image_out, h->n_contrib, h->accum_alpha, covis, uncert, s);
+    }
+    CK(cudaGetLastError());
+    if (n_rendered) *n_rendered = m;
+    h->fwd_valid = true;
+    return GSR_OK;
+}
+
+int gsr_backward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K, const float *means,
+                 const float *shs, const float *opacities, const float *scales, const float *rotations,
+                 const float background[3], const float *vpixels, float *vmeans, float *vshs, float *vopacities,
+                 float *vscales, float *vrot, float *vR, float *vt, int32_t accumulate, void *stream) {
+    if (!h) return GSR_EINVAL;
+    (void)opacities;  // opacity is read from the packed record written by the forward
+    if (!cam || !background || !vpixels || !vmeans || !vshs || !vopacities || !vscales || !vrot)
+        return fail(h, GSR_EINVAL, "gsr_backward: null argument");
+    if (!h->fwd_valid || n != h->last_n)
+        return fail(h, GSR_ESTATE, "gsr_backward: no matching gsr_forward on this handle");
+    if ((vR == nullptr) != (vt == nullptr)) return fail(h, GSR_EINVAL, "gsr_backward: pass both vR and vt or neither");
+    if (sh_degree < 0 || sh_degree > 3 || K < (sh_degree + 1) * (sh_degree + 1))
+        return fail(h, GSR_EINVAL, "gsr_backward: need 0 <= sh_degree <= 3 and K >= (sh_degree+1)^2");
+    if ((reinterpret_cast<uintptr_t>(rotations) & 15) || (reinterpret_cast<uintptr_t>(vrot) & 15))
+        return fail(h, GSR_EINVAL, "gsr_backward: rotations / vrot must be 16-byte aligned");
+    if (n == 0) return GSR_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int ch = h->cfg.channels;
+    DevCamera dc;
+    make_dev_camera(h, cam, &dc);
+    if (h->last_m > 0) {
+        {
+            StageTimer tm(h, s, GSR_STAGE_ZERO_GRADS);
+            CK(cudaMemsetAsync(h->g.gacc, 0, (size_t)n * acc_floats(ch) * sizeof(float), s));
+        }
+        StageTimer tm(h, s, GSR_STAGE_RENDER_BWD);
+        float bg[8] = {background[0], background[1], background[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+        launch_render_backward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,
+                               bg, vpixels, h->n_contrib, h->accum_alpha, h->g.gacc, s);
+    }
+    {
+        StageTimer tm(h, s, GSR_STAGE_GAUSS_BWD);
+        launch_backward_gaussians(dc, n, sh_degree, K, ch, means, shs, scales, rotations, h->g, vmeans, vshs,
+                                  vopacities, vscales, vrot, vR, vt, accumulate, s);
+    }
+    CK(cudaGetLastError());
+    return GSR_OK;
+}
+
+int gsr_update_stats(GsrHandle *h, int64_t n, int32_t *max_radii, float *accum_grad_means2d, float *denom,
+                     void *stream) {
+    if (!h) return GSR_EINVAL;
+    if (!max_radii || !accum_grad_means2d || !denom) return fail(h, GSR_EINVAL, "gsr_update_stats: null argument");
+    if (n > h->last_n) return fail(h, GSR_ESTATE, "gsr_update_stats: n exceeds the last forward");
+    launch_update_stats(n, h->g.radii, h->g.grad_means2d, (uint32_t)h->cfg.width, (uint32_t)h->cfg.height, max_radii,
+                        accum_grad_means2d, denom, static_cast<cudaStream_t>(stream));
+    CK(cudaGetLastError());
+    return GSR_OK;
+}
+
+int gsr_forward_backward_host(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K,
+                              const float *means_h, const float *shs_h, const float *opacities_h,
+                              const float *scales_h, const float *rotations_h, const float background[3],
+                              const float *vpixels_h, float *image_h, float *vmeans_h, float *vshs_h,
+                              float *vopacities_h, float *vscales_h, float *vrot_h, int64_t *n_rendered,
+                              void *stream) {
+    if (!h) return GSR_EINVAL;
+    if (!means_h || !shs_h || !opacities_h || !scales_h || !rotations_h || !vpixels_h)
+        return fail(h, GSR_EINVAL, "gsr_forward_backward_host: null input");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t f = sizeof(float), N = (size_t)n;
+    const size_t img = (size_t)h->cfg.channels * h->cfg.width * h->cfg.height * f;
+    int rc;
+    if ((rc = ensure_stage(h, h->st_means, 3 * N * f)) || (rc = ensure_stage(h, h->st_shs, 3 * (size_t)K * N * f)) ||
+        (rc = ensure_stage(h, h->st_opac, N * f)) || (rc = ensure_stage(h, h->st_scales, 3 * N * f)) ||
+        (rc = ensure_stage(h, h->st_rots, 4 * N * f)) || (rc = ensure_stage(h, h->st_vpix, img)) ||
+        (rc = ensure_stage(h, h->st_image, img)) || (rc = ensure_stage(h, h->st_vmeans, 3 * N * f)) ||
+        (rc = ensure_stage(h, h->st_vshs, 3 * (size_t)K * N * f)) || (rc = ensure_stage(h, h->st_vopac, N * f)) ||
+        (rc = ensure_stage(h, h->st_vscales, 3 * N * f)) || (rc = ensure_stage(h, h->st_vrot, 4 * N * f)))
+        return rc;
+    CK(cudaMemcpyAsync(h->st_means.p, means_h, 3 * N * f, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->st_scales.p, scales_h, 3 * N * f, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->st_rots.p, rotations_h, 4 * N * f, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->st_opac.p, opacities_h, N * f, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->st_shs.p, shs_h, 3 * (size_t)K * N * f, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->st_vpix.p, vpixels_h, img, cudaMemcpyHostToDevice, s));
+    auto F = [](DevBuf &b) { return static_cast<float *>(b.p); };
+    rc = gsr_forward(h, cam, n, sh_degree, K, F(h->st_means), F(h->st_shs), F(h->st_opac), F(h->st_scales),
+                     F(h->st_rots), background, F(h->st_image), nullptr, nullptr, n_rendered, stream);
+    if (rc) return rc;
+    if (image_h) CK(cudaMemcpyAsync(image_h, h->st_image.p, img, cudaMemcpyDeviceToHost, s));
+    rc = gsr_backward(h, cam, n, sh_degree, K, F(h->st_means), F(h->st_shs), F(h->st_opac), F(h->st_scales),
+                      F(h->st_rots), background, F(h->st_vpix), F(h->st_vmeans), F(h->st_vshs), F(h->st_vopac),
+                      F(h->st_vscales), F(h->st_vrot), nullptr, nullptr, 0, stream);
+    if (rc) return rc;
+    if (vmeans_h) CK(cudaMemcpyAsync(vmeans_h, h->st_vmeans.p, 3 * N * f, cudaMemcpyDeviceToHost, s));
+    if (vshs_h) CK(cudaMemcpyAsync(vshs_h, h->st_vshs.p, 3 * (size_t)K * N * f, cudaMemcpyDeviceToHost, s));
+    if (vopacities_h) CK(cudaMemcpyAsync(vopacities_h, h->st_vopac.p, N * f, cudaMemcpyDeviceToHost, s));
+    if (vscales_h) CK(cudaMemcpyAsync(vscales_h, h->st_vscales.p, 3 * N * f, cudaMemcpyDeviceToHost, s));
+    if (vrot_h) CK(cudaMemcpyAsync(vrot_h, h->st_vrot.p, 4 * N * f, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return GSR_OK;
+}
+
+int gsr_profile_enable(GsrHandle *h, int32_t enable) {
+    if (!h) return GSR_EINVAL;
+    if (enable && !h->ev[0])
+        for (cudaEvent_t &e : h->ev) CK(cudaEventCreate(&e));
+    h->profile = enable != 0;
+    for (bool &u : h->ev_used) u = false;
+    return GSR_OK;
+}
+
+int gsr_profile_get(GsrHandle *h, float ms[GSR_NUM_STAGES]) {
+    if (!h || !ms) return GSR_EINVAL;
+    for (int k = 0; k < GSR_NUM_STAGES; k++) {
+        ms[k] = 0.f;
+        if (h->profile && h->ev_used[k]) {
+            CK(cudaEventSynchronize(h->ev[2 * k + 1]));
+            CK(cudaEventElapsedTime(&ms[k], h->ev[2 * k], h->ev[2 * k + 1]));
+        }
+    }
+    return GSR_OK;
+}
+
+int gsr_measure_fp32_peak(double *tflops, void *stream) {
+    if (!tflops) return GSR_EINVAL;
+    double ms = 0.0, flops = 0.0;
+    if (launch_fp32_peak(static_cast<cudaStream_t>(stream), &ms, &flops) != 0) return GSR_ECUDA;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return GSR_OK;
+}
+
+int gsr_identify_tile_range(const uint64_t *keys_dev, int64_t m, uint32_t *ranges_dev, void *stream) {
+    if (m < 0 || (m > 0 && (!keys_dev || !ranges_dev))) return GSR_EINVAL;
+    launch_tile_ranges(m, keys_dev, ranges_dev, static_cast<cudaStream_t>(stream));
+    return cudaGetLastError() == cudaSuccess ? GSR_OK : GSR_ECUDA;
+}
+
+int gsr_sort_pairs(GsrHandle *h, const uint64_t *keys_in_dev, const uint32_t *vals_in_dev, int64_t m,
+                   uint64_t *keys_out_dev, uint32_t *vals_out_dev, void *stream) {
+    if (!h) return GSR_EINVAL;
+    if (m < 0 || m >= (1ll << 30)) return fail(h, GSR_EINVAL, "gsr_sort_pairs: m out of range");
+    if (m == 0) return GSR_OK;
+    if (!keys_in_dev || !vals_in_dev || !keys_out_dev || !vals_out_dev)
+        return fail(h, GSR_EINVAL, "gsr_sort_pairs: null argument");
+    int rc = ensure_binning(h, m);
+    if (rc) return rc;
+    launch_sort_pairs(h->plan, m, keys_in_dev, vals_in_dev, keys_out_dev, vals_out_dev, h->keys_tmp, h->vals_tmp,
+                      h->sort_temp, static_cast<cudaStream_t>(stream));
+    CK(cudaGetLastError());
+    return GSR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+"""ctypes binding of libgsrast.so (include/gsrast.h).  1:1 with the `ccall`s of julia/GsrastCUDAExt.jl.
+
+The library is built in-tree (csrc/Makefile, nvcc sm_100a).  There is no fallback: if it cannot be
+loaded, importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
+LIB_PATH = os.path.join(CSRC, "libgsrast.so")
+
+GSR_OK, GSR_EINVAL, GSR_ECUDA, GSR_ENOMEM, GSR_ESTATE = 0, -1, -2, -3, -4
+MATH_REFERENCE, MATH_FAST = 0, 1
+
+
+class GsrConfig(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32), ("near_plane", C.c_float),
+                ("far_plane", C.c_float), ("radius_clip", C.c_int32), ("blur_eps", C.c_float),
+                ("math_mode", C.c_int32)]
+
+
+class GsrCamera(C.Structure):
+    _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3), ("focal", C.c_float * 2), ("principal", C.c_float * 2),
+                ("cam_center", C.c_float * 3), ("R_dev", C.c_void_p), ("t_dev", C.c_void_p)]
+
+
+class GsrStateViews(C.Structure):
+    _fields_ = [("n", C.c_int64), ("n_rendered", C.c_int64)] + [(k, C.c_void_p) for k in (
+        "radii", "grad_means2d", "means2d", "depths", "conics", "rgbs", "clamped", "tiles_touched", "points_offset",
+        "normals", "keys_unsorted", "values_unsorted", "keys_sorted", "values_sorted", "ranges", "n_contrib",
+        "accum_alpha")]
+
+
+EXPORTS = ["gsr_version", "gsr_last_error", "gsr_create", "gsr_destroy", "gsr_release_scene_buffers",
+           "gsr_memory_usage", "gsr_get_state", "gsr_forward", "gsr_backward", "gsr_update_stats",
+           "gsr_forward_backward_host", "gsr_identify_tile_range", "gsr_sort_pairs", "gsr_launch_count",
+           "gsr_profile_enable", "gsr_profile_get", "gsr_measure_fp32_peak"]
+STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "render_fwd", "zero_grads", "render_bwd", "gauss_bwd"]
+
+
+def build(force: bool = False) -> str:
+    """Compile libgsrast.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "gsrast.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        cmd = ["make", "-C", CSRC, "-j8"] + (["-B"] if force else [])
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building libgsrast.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    return LIB_PATH
+
+
+def load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.gsr_version.restype = C.c_char_p
+    lib.gsr_last_error.restype = C.c_char_p
+    lib.gsr_last_error.argtypes = [vp]
+    lib.gsr_create.argtypes = [C.POINTER(GsrConfig), C.POINTER(vp)]
+    lib.gsr_destroy.argtypes = [vp]
+    lib.gsr_release_scene_buffers.argtypes = [vp]
+    lib.gsr_memory_usage.argtypes = [vp, C.POINTER(C.c_size_t)]
+    lib.gsr_get_state.argtypes = [vp, C.POINTER(GsrStateViews)]
+    lib.gsr_forward.argtypes = [vp, C.POINTER(GsrCamera), i64, i32, i32, vp, vp, vp, vp, vp, C.POINTER(C.c_float),
+                                vp, vp, vp, C.POINTER(i64), vp]
+    lib.gsr_backward.argtypes = [vp, C.POINTER(GsrCamera), i64, i32, i32, vp, vp, vp, vp, vp, C.POINTER(C.c_float),
+                                 vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.gsr_update_stats.argtypes = [vp, i64, vp, vp, vp, vp]
+    lib.gsr_forward_backward_host.argtypes = [vp, C.POINTER(GsrCamera), i64, i32, i32, vp, vp, vp, vp, vp,
+                                              C.POINTER(C.c_float), vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), vp]
+    lib.gsr_identify_tile_range.argtypes = [vp, i64, vp, vp]
+    lib.gsr_sort_pairs.argtypes = [vp, vp, vp, i64, vp, vp, vp]
+    lib.gsr_launch_count.restype = i64
+    lib.gsr_profile_enable.argtypes = [vp, i32]
+    lib.gsr_profile_get.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.gsr_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), vp]
+    for name in EXPORTS:
+        getattr(lib, name)  # every symbol of include/gsrast.h must resolve
+    return lib
+
+
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = load()
+    return _LIB
+
+
+class GsrError(RuntimeError):
+    pass
+
+
+def check(rc: int, handle=None):
+    if rc != GSR_OK:
+        msg = lib().gsr_last_error(handle)
+        raise GsrError(f"libgsrast error {rc}: {msg.decode() if msg else ''}")

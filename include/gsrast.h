@@ -1,0 +1,190 @@
+/*
+ * gsrast.h — C ABI of libgsrast.so: the sm_100a rasterizer hot path of GaussianSplatting.jl.
+ *
+ * Drop-in boundary.  The reference has no FFI: its operator surface is the Julia pair
+ *     rasterize(means_3d, shs, opacities, scales, rotations, R_w2c, t_w2c; rast, camera, sh_degree,
+ *               background, covisibilities, uncertainties)          src/rasterization/rasterizer.jl:255-408
+ *     ChainRulesCore.rrule(::typeof(rasterize), ...) -> ∇rasterize   src/rasterization/rasterizer.jl:416-573
+ * plus the state other components read (rast.gstate.radii, rast.gstate.∇means_2d — src/strategy.jl:85-86)
+ * and `_update_stats!` (src/strategy.jl:118-136).  ext/GaussianSplattingCUDAExt would `ccall` the entry
+ * points below in place of the KernelAbstractions kernel launches (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every pointer named *_dev / documented "device" is a CUDA device pointer owned by the caller;
+ *   - arrays use the reference's memory layout unchanged (Julia column-major): means (3,N) = N packed
+ *     float[3]; rotations (4,N) wxyz, 16-byte aligned; shs (3,K,N); image (C,W,H) = H rows × W × C;
+ *   - every function returns 0 on success or a negative GsrStatus; the message is at gsr_last_error();
+ *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); a forward performs
+ *     exactly one stream synchronisation (the 4-byte n_rendered read, as rasterizer.jl:337 does);
+ *   - a handle is re-entrant but not thread-safe; handles are independent (two rasterizers coexist when
+ *     a sky dome is used, src/sky_dome.jl:143-145);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with GSR_ECUDA.
+ */
+#ifndef GSRAST_H
+#define GSRAST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GSR_API __attribute__((visibility("default")))
+#else
+#define GSR_API
+#endif
+
+typedef enum {
+    GSR_OK = 0,
+    GSR_EINVAL = -1, /* bad argument (e.g. width % 16 != 0 — rasterizer.jl:66,281,435) */
+    GSR_ECUDA = -2,  /* CUDA runtime / launch failure */
+    GSR_ENOMEM = -3, /* workspace allocation failed */
+    GSR_ESTATE = -4  /* backward without a matching forward on this handle */
+} GsrStatus;
+
+/* math_mode values */
+#define GSR_MATH_REFERENCE 0 /* compositing in the reference's op order, no FMA contraction, expf()      */
+#define GSR_MATH_FAST 1      /* contracted FMAs + ex2.approx in the compositing kernels (same tolerances) */
+
+/* Constructor arguments of `GaussianRasterizer(kab; width, height, mode, near_plane, far_plane)`
+ * (rasterizer.jl:60-90) plus the constants `rasterize` hard-codes (rasterizer.jl:294-295). */
+typedef struct {
+    int32_t width;       /* multiple of 16 */
+    int32_t height;      /* multiple of 16 */
+    int32_t channels;    /* 3 = :rgb, 5 = :rgbd, 8 = :rgbdn (rasterizer.jl:47-51) */
+    float near_plane;    /* 0.2f */
+    float far_plane;     /* 1000.f */
+    int32_t radius_clip; /* 3 */
+    float blur_eps;      /* 0.3f */
+    int32_t math_mode;   /* GSR_MATH_* */
+} GsrConfig;
+
+/* The fields of `Camera` the path reads (src/camera.jl:2-45; rasterizer.jl:285-291, 310, 321). */
+typedef struct {
+    float R[9];           /* w2c[1:3,1:3], column-major */
+    float t[3];           /* w2c[1:3,4] */
+    float focal[2];
+    float principal[2];   /* in [0,1] */
+    float cam_center[3];  /* c2w[1:3,4] */
+    const float *R_dev;   /* optional device (3,3) column-major / (3,) arrays: the positional R_w2c, t_w2c */
+    const float *t_dev;   /* of `rasterize` (pose optimisation, projection.jl:71-75); NULL = use R, t    */
+} GsrCamera;
+
+/* Device views of the handle-owned state (GeometryState / BinningState / ImageState, states.jl).
+ * Valid until the next gsr_forward / gsr_release_scene_buffers / gsr_destroy on the handle. */
+typedef struct {
+    int64_t n;                      /* Gaussians of the last forward */
+    int64_t n_rendered;             /* tile instances M of the last forward */
+    const int32_t *radii;           /* [n]   rast.gstate.radii */
+    float *grad_means2d;            /* [n,2] rast.gstate.∇means_2d (pixel units), written by gsr_backward */
+    const float *means2d;           /* [n,2] */
+    const float *depths;            /* [n] */
+    const float *conics;            /* [n,3] conic_opacities */
+    const float *rgbs;              /* [n,3] */
+    const uint8_t *clamped;         /* [n,3] */
+    const int32_t *tiles_touched;   /* [n] */
+    const int32_t *points_offset;   /* [n] inclusive scan */
+    const float *normals;           /* [n,3] (channels == 8) or NULL */
+    const uint64_t *keys_unsorted;  /* [M] */
+    const uint32_t *values_unsorted;/* [M] 1-based ids */
+    const uint64_t *keys_sorted;    /* [M] */
+    const uint32_t *values_sorted;  /* [M] */
+    const uint32_t *ranges;         /* [T,2] start (0-based), end (exclusive) */
+    const uint32_t *n_contrib;      /* [H,W] */
+    const float *accum_alpha;       /* [H,W] */
+} GsrStateViews;
+
+typedef struct GsrHandle GsrHandle;
+
+GSR_API const char *gsr_version(void);
+GSR_API const char *gsr_last_error(const GsrHandle *h); /* h may be NULL: last error of a failed gsr_create */
+
+/* GaussianRasterizer(kab; ...) — rasterizer.jl:60-90 */
+GSR_API int gsr_create(const GsrConfig *cfg, GsrHandle **out);
+/* KA.unsafe_free!(rast) — rasterizer.jl:136-145 */
+GSR_API int gsr_destroy(GsrHandle *h);
+/* release_scene_buffers!(rast) — rasterizer.jl:111-123 */
+GSR_API int gsr_release_scene_buffers(GsrHandle *h);
+/* memory_usage(rast) — rasterizer.jl:127-134 (workspace bytes owned by the handle) */
+GSR_API int gsr_memory_usage(const GsrHandle *h, size_t *bytes);
+GSR_API int gsr_get_state(const GsrHandle *h, GsrStateViews *views);
+
+/* rasterize(...) — rasterizer.jl:255-408.
+ *   n, K          Gaussians, stored SH coefficients per Gaussian ((max_sh_degree+1)^2); sh_degree in [0,3]
+ *   means/scales  device (3,n); rotations device (4,n) 16-byte aligned; opacities device (1,n) activated;
+ *                 shs device (3,K,n)
+ *   background    host float[3]
+ *   image_out     device (channels,W,H), fully overwritten (zero image when n_rendered == 0, rasterizer.jl:338)
+ *   covis         optional device bool[n]  (render.jl:112)   uncert: optional device float (W,H) (render.jl:109,128)
+ *   n_rendered    optional host out
+ */
+GSR_API int gsr_forward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K, const float *means,
+                const float *shs, const float *opacities, const float *scales, const float *rotations,
+                const float background[3], float *image_out, uint8_t *covis, float *uncert, int64_t *n_rendered,
+                void *stream);
+
+/* ∇rasterize(...) — rasterizer.jl:416-550, for the forward last run on this handle with the same inputs.
+ *   vpixels       device (channels,W,H)
+ *   vmeans (3,n), vshs (3,K,n), vopacities (1,n), vscales (3,n), vrot (4,n): device outputs, fully written
+ *   (zeros for culled Gaussians) when accumulate == 0, added to when accumulate != 0 (view batches);
+ *   vR (3,3 column-major) / vt (3): optional device outputs of the pose path (projection.jl:243-256),
+ *   always accumulated into (caller zero-fills, as rasterizer.jl:500-501 does).
+ */
+GSR_API int gsr_backward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K, const float *means,
+                 const float *shs, const float *opacities, const float *scales, const float *rotations,
+                 const float background[3], const float *vpixels, float *vmeans, float *vshs, float *vopacities,
+                 float *vscales, float *vrot, float *vR, float *vt, int32_t accumulate, void *stream);
+
+/* update_stats!(strategy, rast.gstate.radii, rast.gstate.∇means_2d, resolution) — strategy.jl:107-136 */
+GSR_API int gsr_update_stats(GsrHandle *h, int64_t n, int32_t *max_radii, float *accum_grad_means2d, float *denom,
+                     void *stream);
+
+/* Host-buffer convenience used for end-to-end timing: copies the five parameter arrays and vpixels from
+ * (pinned) host memory, runs forward + backward, copies image and gradients back; one synchronisation at
+ * the end.  Any of the host output pointers may be NULL. */
+GSR_API int gsr_forward_backward_host(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K,
+                              const float *means_h, const float *shs_h, const float *opacities_h,
+                              const float *scales_h, const float *rotations_h, const float background[3],
+                              const float *vpixels_h, float *image_h, float *vmeans_h, float *vshs_h,
+                              float *vopacities_h, float *vscales_h, float *vrot_h, int64_t *n_rendered,
+                              void *stream);
+
+/* Stand-alone stages (known-answer tests of the reference: runtests.jl:486-494; sort yardstick). */
+/* identify_tile_range!(ranges, keys) — utils.jl:56-78; ranges_dev (2,T) must be pre-zeroed by the caller. */
+GSR_API int gsr_identify_tile_range(const uint64_t *keys_dev, int64_t m, uint32_t *ranges_dev, void *stream);
+/* stable ascending sort of (key,value) pairs on the `tile_bits + depth bits` that can differ
+ * (sortperm! + 2×_permute!, rasterizer.jl:357-372).  depth bits are taken relative to bits(near) when near > 0. */
+GSR_API int gsr_sort_pairs(GsrHandle *h, const uint64_t *keys_in_dev, const uint32_t *vals_in_dev, int64_t m,
+                   uint64_t *keys_out_dev, uint32_t *vals_out_dev, void *stream);
+
+/* Per-stage device timing (CUDA events on the caller's stream; SURVEY.md §5 "tracing / profiling").
+ * When enabled, gsr_forward / gsr_backward bracket each stage with events; gsr_profile_get synchronises on
+ * them and returns the durations of the last forward + backward in milliseconds (0 for stages that did not run). */
+enum {
+    GSR_STAGE_PREPROCESS = 0, /* project! + spherical_harmonics! + count_tiles + feature packing */
+    GSR_STAGE_SCAN,           /* cumsum! + n_rendered read-back */
+    GSR_STAGE_DUPLICATE,      /* duplicate_with_keys! */
+    GSR_STAGE_SORT,           /* sortperm! + 2 x _permute! */
+    GSR_STAGE_RANGES,         /* fill!(ranges) + identify_tile_range! */
+    GSR_STAGE_RENDER_FWD,     /* render! */
+    GSR_STAGE_ZERO_GRADS,     /* zero-fill of the per-Gaussian accumulators */
+    GSR_STAGE_RENDER_BWD,     /* ∇render! */
+    GSR_STAGE_GAUSS_BWD,      /* ∇project! + ∇spherical_harmonics! */
+    GSR_NUM_STAGES
+};
+GSR_API int gsr_profile_enable(GsrHandle *h, int32_t enable);
+GSR_API int gsr_profile_get(GsrHandle *h, float ms[GSR_NUM_STAGES]);
+
+/* FP32 FMA micro-benchmark on the current device (dependent FFMA chains, all SMs): the measured FP32 peak
+ * that the compositing kernels' roofline fraction is quoted against. */
+GSR_API int gsr_measure_fp32_peak(double *tflops, void *stream);
+
+/* Kernels launched by this library since process start (bench.py's gpu_launches). */
+GSR_API int64_t gsr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSRAST_H */

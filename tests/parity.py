@@ -1,0 +1,167 @@
+"""Shared helpers of the `-m gpu` parity tests: run the CUDA path through the C ABI (via the gsrast
+binding), run the CPU oracle on the same seeded inputs, and compare with the tolerances north_star states.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8d):
+  * projection, sort keys, tile ranges (and every integer buffer): BIT-EXACT;
+  * forward image / accum_alpha / uncertainties: <= 1e-5 absolute (the depth channel, whose values reach
+    tens of units where one fp32 ulp is ~2e-6, is held to 1e-5 * max(1, |depth|));
+  * gradients: <= 1e-4 relative  (||Δ||∞ / ||ref||∞ per tensor).
+Pixels where the oracle saw a pair within `AMBIG_REL` of one of the kernel's branch thresholds
+(σ<0, α<1/255, T'<1e-4) may legitimately take the other branch when exp() differs by an ulp
+(libdevice expf vs glibc expf); they are excluded from the 1e-5 check, counted, and bounded.
+"""
+import numpy as np
+import torch
+
+from oracle.oracle import Oracle, OracleCamera
+from gsrast import Camera, GaussianRasterizer
+
+AMBIG_REL = 2e-5
+IMG_ATOL = 1e-5
+GRAD_RTOL = 1e-4
+CH = {"rgb": 3, "rgbd": 5, "rgbdn": 8}
+
+_ORACLES = {}
+
+
+def oracle(dtype=np.float32):
+    if dtype not in _ORACLES:
+        _ORACLES[dtype] = Oracle(dtype)
+    return _ORACLES[dtype]
+
+
+def cameras(scene_or_dims, fx=None, fy=None, R=None, t=None, principal=(0.5, 0.5)):
+    if hasattr(scene_or_dims, "fx"):
+        W, H, fx, fy = scene_or_dims.width, scene_or_dims.height, scene_or_dims.fx, scene_or_dims.fy
+    else:
+        W, H = scene_or_dims
+    R = np.eye(3, dtype=np.float32) if R is None else np.asarray(R, np.float32)
+    t = np.zeros(3, np.float32) if t is None else np.asarray(t, np.float32)
+    cam = Camera(fx=float(fx), fy=float(fy), width=W, height=H, R=R, t=t, principal=tuple(principal))
+    ocam = OracleCamera(R.astype(np.float64), t.astype(np.float64), np.array([fx, fy], np.float64),
+                        np.array(principal, np.float64), cam.camera_center.astype(np.float64), W, H)
+    return cam, ocam
+
+
+def to_dev(sc):
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return dict(means=d(sc.means), shs=d(sc.shs), opac=d(sc.opacities.reshape(-1, 1)), scales=d(sc.scales),
+                rots=d(sc.rotations))
+
+
+def gpu_forward(rast, dev, cam, sh_degree, background=(0, 0, 0), covis=None, uncert=None, R_w2c=None, t_w2c=None):
+    img = rast._forward(dev["means"], dev["shs"], dev["opac"], dev["scales"], dev["rots"], R_w2c, t_w2c, cam,
+                        sh_degree, background, covis, uncert)
+    torch.cuda.synchronize()
+    return img
+
+
+def gpu_backward(rast, dev, cam, sh_degree, vpix, background=(0, 0, 0), R_w2c=None, t_w2c=None, **kw):
+    g = rast._backward(vpix, dev["means"], dev["shs"], dev["opac"], dev["scales"], dev["rots"], R_w2c, t_w2c, cam,
+                       sh_degree, background, **kw)
+    torch.cuda.synchronize()
+    return g
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def assert_forward_state_bit_exact(rast, st, n):
+    """Every per-Gaussian / per-instance / per-tile buffer of the forward against the oracle, bit for bit."""
+    gs = rast.gstate
+    radii = np_(gs.radii)
+    assert (radii == st.radii[:n]).all(), f"radii differ at {np.flatnonzero(radii != st.radii[:n])[:10]}"
+    vis = radii > 0
+    for name, got, ref in (("means2d", gs.means2d, st.means2d), ("depths", gs.depths, st.depths),
+                           ("conics", gs.conics, st.conics), ("rgbs", gs.rgbs, st.rgbs)):
+        a = np_(got)[vis].view(np.uint32)
+        b = np.ascontiguousarray(ref[:n][vis]).view(np.uint32)
+        bad = np.flatnonzero((a != b).reshape(len(a), -1).any(1))
+        assert bad.size == 0, f"{name}: {bad.size} visible rows differ bitwise, first {bad[:5]}"
+    assert (np_(gs.clamped)[vis] == st.clamped[:n][vis]).all()
+    assert (np_(gs.tiles_touched) == st.tiles_touched[:n]).all()
+    assert (np_(gs.points_offset) == st.points_offset[:n]).all()
+    if st.normals is not None:
+        assert (np_(gs.normals)[vis].view(np.uint32) == st.normals[:n][vis].view(np.uint32)).all()
+    assert gs.n_rendered == st.n_rendered
+    if st.n_rendered:
+        assert (np_(gs.keys_unsorted).view(np.uint64) == st.keys_unsorted).all()
+        assert (np_(gs.values_unsorted).view(np.uint32) == st.values_unsorted).all()
+        assert (np_(gs.keys_sorted).view(np.uint64) == st.keys_sorted).all()
+        assert (np_(gs.values_sorted).view(np.uint32) == st.values_sorted).all()
+        assert (np_(gs.ranges).view(np.uint32) == st.ranges).all()
+
+
+def assert_image_close(img, st, ref_img, uncert=None, ref_uncert=None, max_ambig_frac=0.02):
+    """1e-5 absolute on every non-ambiguous pixel; ambiguous ones are bounded by one flipped pair."""
+    img = np_(img)
+    C = img.shape[2]
+    ok = st.ambiguous == 0
+    assert (1.0 - ok.mean()) <= max_ambig_frac, f"ambiguous fraction {1 - ok.mean():.4f}"
+    d = np.abs(img.astype(np.float64) - ref_img.astype(np.float64))
+    tol = np.full(C, IMG_ATOL)
+    tolmap = np.broadcast_to(tol, d.shape).copy()
+    if C > 3:
+        tolmap[:, :, 3] = IMG_ATOL * np.maximum(1.0, np.abs(ref_img[:, :, 3]))  # depth channel, see module doc
+    bad = (d > tolmap) & ok[:, :, None]
+    assert not bad.any(), (f"{bad.sum()} non-ambiguous values beyond 1e-5: max err {d[ok].max():.3e} "
+                           f"at {np.argwhere(bad)[:5].tolist()}")
+    scale = max(1.0, float(np.abs(ref_img).max()))
+    assert d.max() <= 2e-2 * scale, f"ambiguous pixel error {d.max():.3e} too large for a single flipped pair"
+    return dict(max_err=float(d[ok].max()) if ok.any() else 0.0, ambiguous=int((~ok).sum()),
+                max_err_ambiguous=float(d.max()))
+
+
+def assert_ncontrib(rast, st, max_mismatch_frac=1e-4):
+    nc = np_(rast.gstate.n_contrib).view(np.uint32)
+    ok = st.ambiguous == 0
+    assert (nc[ok] == st.n_contrib[ok]).all(), "n_contrib differs on non-ambiguous pixels"
+    T = np_(rast.gstate.accum_alpha)
+    assert np.abs(T[ok] - st.accum_alpha[ok]).max() <= IMG_ATOL
+    return float((nc != st.n_contrib).mean())
+
+
+def rel_err(a, ref):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def assert_grads_close(g, ref, rtol=GRAD_RTOL, keys=("vmeans", "vshs", "vopacities", "vscales", "vrot")):
+    out = {}
+    for k in keys:
+        a = np_(g[k]).reshape(ref[k].shape) if isinstance(g[k], torch.Tensor) else g[k]
+        assert np.isfinite(a).all(), f"{k} has non-finite values"
+        out[k] = rel_err(a, ref[k])
+        assert out[k] <= rtol, f"{k}: relative error {out[k]:.3e} > {rtol:g}"
+    return out
+
+
+def run_case(sc, mode, math_mode="reference", background=(0, 0, 0), R=None, t=None, principal=(0.5, 0.5),
+             check_backward=True, near=0.2, far=1000.0, vpix_seed=1, grad_rtol=GRAD_RTOL):
+    """Full forward(+backward) parity of one scene; returns a dict of measured errors."""
+    from gsrast.synthetic import make_vpixels
+    cam, ocam = cameras(sc, R=R, t=t, principal=principal)
+    dev = to_dev(sc)
+    rast = GaussianRasterizer(width=sc.width, height=sc.height, mode=mode, math_mode=math_mode, near_plane=near,
+                              far_plane=far)
+    img = gpu_forward(rast, dev, cam, sc.sh_degree, background)
+    o = oracle()
+    ref_img, st = o.forward(sc.means, sc.shs, sc.opacities, sc.scales, sc.rotations, ocam, mode=mode,
+                            sh_degree=sc.sh_degree, background=background, near=near, far=far, ambig_rel=AMBIG_REL)
+    assert_forward_state_bit_exact(rast, st, sc.n)
+    res = {}
+    if st.n_rendered:
+        res.update(assert_image_close(img, st, ref_img))
+        res["ncontrib_mismatch"] = assert_ncontrib(rast, st)
+    else:
+        assert (np_(img) == 0).all()
+    if check_backward:
+        vp = make_vpixels(sc.width, sc.height, CH[mode], vpix_seed)
+        g = gpu_backward(rast, dev, cam, sc.sh_degree, torch.from_numpy(vp).cuda(), background)
+        ref = o.backward(vp, sc.means, sc.shs, sc.opacities, sc.scales, sc.rotations, ocam, st, mode=mode,
+                         sh_degree=sc.sh_degree, background=background)
+        res.update(assert_grads_close(g, ref, rtol=grad_rtol))
+        res["grad_means2d"] = rel_err(np_(rast.gstate.grad_means2d), ref["vmeans2d"])
+        assert res["grad_means2d"] <= grad_rtol
+    return res, rast, st
