@@ -215,6 +215,38 @@ class GaussianRasterizer:
         return outs
 
 
+    def forward_backward_host(self, host: dict, vpixels_h, camera: Camera, sh_degree: int, background=(0.0, 0.0, 0.0),
+                              out: dict | None = None):
+        """gsr_forward_backward_host: inputs / outputs are HOST (ideally pinned) float32 torch tensors or NumPy
+        arrays; H2D of the five parameter arrays + vpixels, forward, backward, D2H of image + gradients."""
+        def hp(a):
+            if a is None:
+                return None
+            return C.c_void_p(a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data)
+        n, K = host["means"].shape[0], host["shs"].shape[1]
+        out = out or {}
+        cam = camera.to_c()
+        bg = (C.c_float * 3)(*[float(b) for b in background])
+        m = C.c_int64(0)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().gsr_forward_backward_host(
+                self._h, C.byref(cam), n, sh_degree, K, hp(host["means"]), hp(host["shs"]), hp(host["opac"]),
+                hp(host["scales"]), hp(host["rots"]), bg, hp(vpixels_h), hp(out.get("image")), hp(out.get("vmeans")),
+                hp(out.get("vshs")), hp(out.get("vopacities")), hp(out.get("vscales")), hp(out.get("vrot")),
+                C.byref(m), stream), self._h)
+        self.n_rendered = int(m.value)
+        return out
+
+    def profile(self, enable: bool):
+        check(_lib.lib().gsr_profile_enable(self._h, int(enable)), self._h)
+
+    def stage_times_ms(self) -> dict:
+        arr = (C.c_float * len(_lib.STAGES))()
+        check(_lib.lib().gsr_profile_get(self._h, arr), self._h)
+        return {k: float(arr[i]) for i, k in enumerate(_lib.STAGES)}
+
+
 class _Rasterize(torch.autograd.Function):
     """`ChainRulesCore.rrule(::typeof(rasterize), ...)` — rasterizer.jl:552-573."""
 
