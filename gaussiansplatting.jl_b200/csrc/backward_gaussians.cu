@@ -68,7 +68,7 @@ template <bool ACC>
 __global__ void __launch_bounds__(BG_THREADS)
 backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_degree, const int K, const int channels,
                           const float *__restrict__ means, const float *__restrict__ shs,
-                          const float *__restrict__ scales, const float *__restrict__ rots, const GeomPtrs g,
+                          const float *__restrict__ opac, const float *__restrict__ scales, const float *__restrict__ rots, const GeomPtrs g,
                           float *__restrict__ vmeans, float *__restrict__ vshs, float *__restrict__ vopac,
                           float *__restrict__ vscales, float *__restrict__ vrot, float *vR_out, float *vt_out) {
     const int64_t i = (int64_t)blockIdx.x * BG_THREADS + threadIdx.x;
@@ -99,9 +99,15 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
             const float4 a0 = *reinterpret_cast<const float4 *>(acc);
             const float4 a1 = *reinterpret_cast<const float4 *>(acc + 4);
             const float4 a2 = *reinterpret_cast<const float4 *>(acc + 8);
-            const float vm2[2] = {a0.x, a0.y};
-            const float vcn[3] = {a0.z, a0.w, a1.x};
-            const float vop = a1.y;
+            // the compositing backward accumulates moments (render.cu): convert to the reference's cotangents
+            //   v_mean2d = conic * (Sx, Sy)             render.jl:269-272
+            //   v_conic  = 0.5 * (Sxx, Sxy, Syy)        render.jl:264-268
+            //   v_opacity = (sum e*v_alpha) / opacity   render.jl:273  (e = opacity*G)
+            const float ca = g.conics[3 * i], cb = g.conics[3 * i + 1], cc = g.conics[3 * i + 2];
+            const float vm2[2] = {ca * a0.x + cb * a0.y, cb * a0.x + cc * a0.y};
+            const float vcn[3] = {0.5f * a0.z, 0.5f * a0.w, 0.5f * a1.x};
+            const float op = opac[i];
+            const float vop = op > 0.0f ? a1.y / op : 0.0f;
             float vcol[8] = {a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, 0.f, 0.f};
             if (channels > 5) {
                 const float4 a3 = *reinterpret_cast<const float4 *>(acc + 12);
@@ -127,7 +133,6 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
             const float4 q4 = *reinterpret_cast<const float4 *>(rots + 4 * i);
 
             // ∇inverse (render.jl:383-385): vΣ2D = -Σ⁻¹ vΣ⁻¹ Σ⁻¹ with symmetric 2x2 operands (projection.jl:178-188)
-            const float ca = g.conics[3 * i], cb = g.conics[3 * i + 1], cc = g.conics[3 * i + 2];
             float vS2[4];  // column-major 2x2
             {
                 const float X[4] = {ca, cb, cb, cc}, V[4] = {vcn[0], vcn[1], vcn[1], vcn[2]};
@@ -458,16 +463,17 @@ int launch_fp32_peak(cudaStream_t s, double *ms, double *flops) {
 }
 
 void launch_backward_gaussians(const DevCamera &cam, int64_t n, int sh_degree, int K, int channels,
-                               const float *means, const float *shs, const float *scales, const float *rots,
+                               const float *means, const float *shs, const float *opac, const float *scales,
+                               const float *rots,
                                const GeomPtrs &g, float *vmeans, float *vshs, float *vopac, float *vscales,
                                float *vrot, float *vR, float *vt, int accumulate, cudaStream_t s) {
     if (n <= 0) return;
     const unsigned blocks = (unsigned)((n + BG_THREADS - 1) / BG_THREADS);
     if (accumulate)
-        backward_gaussians_kernel<true><<<blocks, BG_THREADS, 0, s>>>(cam, n, sh_degree, K, channels, means, shs, scales,
+        backward_gaussians_kernel<true><<<blocks, BG_THREADS, 0, s>>>(cam, n, sh_degree, K, channels, means, shs, opac, scales,
                                                                      rots, g, vmeans, vshs, vopac, vscales, vrot, vR, vt);
     else
-        backward_gaussians_kernel<false><<<blocks, BG_THREADS, 0, s>>>(cam, n, sh_degree, K, channels, means, shs, scales,
+        backward_gaussians_kernel<false><<<blocks, BG_THREADS, 0, s>>>(cam, n, sh_degree, K, channels, means, shs, opac, scales,
                                                                       rots, g, vmeans, vshs, vopac, vscales, vrot, vR, vt);
     count_launch();
 }

@@ -29,8 +29,8 @@ struct DevCamera {
 //   float4 q2 = {f2, f3, f4, f5}            (channels <= 6 -> 3 quads, 48 B)
 //   float4 q3 = {f6, f7, 0, 0}              (channels == 8 -> 4 quads, 64 B)
 __host__ __device__ constexpr int rec_quads(int channels) { return channels <= 6 ? 3 : 4; }
-// Per-Gaussian gradient accumulator filled by the backward compositing kernel (same quad count):
-//   {v_mean2d.x, v_mean2d.y, v_conic.a, v_conic.b, v_conic.c, v_opacity, v_f0 ... v_f(C-1), pad}
+// Per-Gaussian gradient accumulator filled by the backward compositing kernel (same quad count), moment form:
+//   {S v_sigma*dx, S v_sigma*dy, S v_sigma*dx^2, S v_sigma*dx*dy, S v_sigma*dy^2, S e*v_alpha, v_f0 ... v_f(C-1), pad}
 __host__ __device__ constexpr int acc_floats(int channels) { return 4 * rec_quads(channels); }
 
 struct GeomPtrs {  // GeometryState (states.jl:2-47), SoA
@@ -82,7 +82,8 @@ void launch_render_backward(int channels, int math_mode, int width, int height, 
                             const uint32_t *n_contrib, const float *accum_alpha, float *gacc, cudaStream_t s);
 
 void launch_backward_gaussians(const DevCamera &cam, int64_t n, int sh_degree, int K, int channels,
-                               const float *means, const float *shs, const float *scales, const float *rots,
+                               const float *means, const float *shs, const float *opac, const float *scales,
+                               const float *rots,
                                const GeomPtrs &g, float *vmeans, float *vshs, float *vopac, float *vscales,
                                float *vrot, float *vR, float *vt, int accumulate, cudaStream_t s);
 

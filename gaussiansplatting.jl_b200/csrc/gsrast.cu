@@ -415,8 +415,7 @@ int gsr_backward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degre
                  const float background[3], const float *vpixels, float *vmeans, float *vshs, float *vopacities,
                  float *vscales, float *vrot, float *vR, float *vt, int32_t accumulate, void *stream) {
     if (!h) return GSR_EINVAL;
-    (void)opacities;  // opacity is read from the packed record written by the forward
-    if (!cam || !background || !vpixels || !vmeans || !vshs || !vopacities || !vscales || !vrot)
+    if (!cam || !background || !vpixels || !vmeans || !vshs || !vopacities || !vscales || !vrot || !opacities)
         return fail(h, GSR_EINVAL, "gsr_backward: null argument");
     if (!h->fwd_valid || n != h->last_n)
         return fail(h, GSR_ESTATE, "gsr_backward: no matching gsr_forward on this handle");
@@ -442,8 +441,8 @@ int gsr_backward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degre
     }
     {
         StageTimer tm(h, s, GSR_STAGE_GAUSS_BWD);
-        launch_backward_gaussians(dc, n, sh_degree, K, ch, means, shs, scales, rotations, h->g, vmeans, vshs,
-                                  vopacities, vscales, vrot, vR, vt, accumulate, s);
+        launch_backward_gaussians(dc, n, sh_degree, K, ch, means, shs, opacities, scales, rotations, h->g, vmeans,
+                                  vshs, vopacities, vscales, vrot, vR, vt, accumulate, s);
     }
     CK(cudaGetLastError());
     return GSR_OK;
