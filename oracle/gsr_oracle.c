@@ -661,12 +661,13 @@ EXPORT void orc_pack_features(int64_t n, int channels, const real *rgbs, const r
  * counts (optional, int64[2]) accumulates evaluated / blended pair counts for the roofline formulas.
  * ambig (optional, per pixel) flags pixels where some pair sits within `ambig_rel` (relative) of one of the
  * kernel's discontinuities (σ<0, α<1/255, T'<1e-4): there a 1-ulp difference in exp() legitimately flips a
- * branch, so parity tests hold those pixels to a looser bound (see tests/parity.py). */
+ * branch, so parity tests hold those pixels to a looser bound (see tests/parity.py).  ambig_g (optional, per
+ * Gaussian) flags the Gaussian of such a pair: its gradient gains or loses that pair's whole contribution. */
 EXPORT void orc_render(int channels, int32_t width, int32_t height, const uint32_t *ranges, const uint32_t *values,
                        const real *means2d, const real *opacities, const real *conics, const real *features,
                        const real *background, real *out_color, uint32_t *n_contrib, real *accum_alpha,
                        uint8_t *covis, real *uncert, int64_t *counts, int32_t tile_y0, int32_t tile_y1,
-                       uint8_t *ambig, real ambig_rel) {
+                       uint8_t *ambig, real ambig_rel, uint8_t *ambig_g) {
     int32_t gx = (width + BLOCK - 1) / BLOCK, gy = (height + BLOCK - 1) / BLOCK;
     if (tile_y1 <= 0 || tile_y1 > gy) tile_y1 = gy;
     if (tile_y0 < 0) tile_y0 = 0;
@@ -690,13 +691,13 @@ EXPORT void orc_render(int channels, int32_t width, int32_t height, const uint32
                         const real *cn = conics + 3 * (int64_t)g;
                         real sigma = (cn[1] * dx) * dy + RC(0.5) * (cn[0] * (dx * dx) + cn[2] * (dy * dy));
                         ev_total++;
-                        if (ambig && R_FABS(sigma) <= ambig_rel) ambig[(int64_t)py * width + px] = 1;
+                        if (ambig && R_FABS(sigma) <= ambig_rel) { ambig[(int64_t)py * width + px] = 1; if (ambig_g) ambig_g[g] = 1; }
                         if (sigma < (real)0) continue;
                         real alpha = rmin_(RC(0.99), opacities[g] * R_EXP(-sigma));
-                        if (ambig && R_FABS(alpha * RC(255.0) - RC(1.0)) <= ambig_rel) ambig[(int64_t)py * width + px] = 1;
+                        if (ambig && R_FABS(alpha * RC(255.0) - RC(1.0)) <= ambig_rel) { ambig[(int64_t)py * width + px] = 1; if (ambig_g) ambig_g[g] = 1; }
                         if (alpha < RC(1.0) / RC(255.0)) continue;
                         real Tt = T * (RC(1.0) - alpha);
-                        if (ambig && R_FABS(Tt * RC(1e4) - RC(1.0)) <= ambig_rel) ambig[(int64_t)py * width + px] = 1;
+                        if (ambig && R_FABS(Tt * RC(1e4) - RC(1.0)) <= ambig_rel) { ambig[(int64_t)py * width + px] = 1; if (ambig_g) ambig_g[g] = 1; }
                         if (Tt < RC(1e-4)) break;
                         const real *f = features + (int64_t)channels * g;
                         for (int c = 0; c < channels; c++) color[c] += (f[c] * alpha) * T;
