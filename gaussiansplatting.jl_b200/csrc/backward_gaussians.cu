@@ -70,19 +70,56 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
                           const float *__restrict__ means, const float *__restrict__ shs,
                           const float *__restrict__ opac, const float *__restrict__ scales, const float *__restrict__ rots, const GeomPtrs g,
                           float *__restrict__ vmeans, float *__restrict__ vshs, float *__restrict__ vopac,
-                          float *__restrict__ vscales, float *__restrict__ vrot, float *vR_out, float *vt_out) {
-    const int64_t i = (int64_t)blockIdx.x * BG_THREADS + threadIdx.x;
+                          float *__restrict__ vscales, float *__restrict__ vrot, float *vR_out, float *vt_out,
+                          const int sh_stride) {
+    // SH coefficients in / SH gradients out are staged through shared memory: the (3,K,n) rows of a CTA's
+    // 128 Gaussians form one contiguous span that is read and written with coalesced 128-bit accesses, while each
+    // thread works on its own padded (odd stride -> conflict-free) row.
+    extern __shared__ float s_sh[];  // [BG_THREADS][sh_stride]
+    const int tid = threadIdx.x;
+    const int64_t block0 = (int64_t)blockIdx.x * BG_THREADS;
+    const int64_t i = block0 + tid;
     const bool pose = vR_out != nullptr;
     float pose_acc[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) pose_acc[k] = 0.f;
+    const int row = 3 * K;
+    const int k_used = (sh_degree + 1) * (sh_degree + 1);
+    const int64_t nb = (n - block0) < BG_THREADS ? (n - block0) : BG_THREADS;
+    const int64_t span = nb * row;
+    const bool visible_t = (i < n) && g.radii[i] > 0;
+    const bool aligned16 = (((uintptr_t)shs | (uintptr_t)vshs) & 15) == 0;
+    if (__syncthreads_or(visible_t) && sh_degree > 0) {
+        if (k_used == K) {
+            const float *src = shs + block0 * row;
+            const int64_t nq = aligned16 ? (span >> 2) : 0;
+            for (int64_t q = tid; q < nq; q += BG_THREADS) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + q);
+                const int e = (int)(q << 2);
+                const int gq = e / row, rq = e - gq * row;
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    int gg = gq, rr = rq + u;
+                    if (rr >= row) { rr -= row; gg += 1; }
+                    s_sh[gg * sh_stride + rr] = vv[u];
+                }
+            }
+            for (int64_t e = (nq << 2) + tid; e < span; e += BG_THREADS) {
+                const int gg = (int)(e / row), rr = (int)(e - (int64_t)gg * row);
+                s_sh[gg * sh_stride + rr] = src[e];
+            }
+        } else if (visible_t) {
+            const float *src = shs + i * (int64_t)row;
+            for (int e = 0; e < 3 * k_used; e++) s_sh[tid * sh_stride + e] = src[e];
+        }
+    }
+    __syncthreads();
 
     if (i < n) {
         const int AF = acc_floats(channels);
-        const bool visible = g.radii[i] > 0;
-        const int row = 3 * K;
-        const int k_used = (sh_degree + 1) * (sh_degree + 1);
-        float *vsh = vshs + i * (int64_t)row;
+        const bool visible = visible_t;
+        float *vsh = s_sh + tid * sh_stride;  // this thread's row: coefficients in, gradients out (in place)
         if (!visible) {
             // projection.jl:172-176: culled rows keep the zero gradient; ∇spherical_harmonics! runs with a zero
             // colour cotangent and also yields zero.
@@ -92,8 +129,8 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
                 for (int k = 0; k < 3; k++) { vmeans[3 * i + k] = 0.f; vscales[3 * i + k] = 0.f; }
                 *reinterpret_cast<float4 *>(vrot + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
                 vopac[i] = 0.f;
-                for (int e = 0; e < row; e++) vsh[e] = 0.f;
             }
+            for (int e = 0; e < row; e++) vsh[e] = 0.f;
         } else {
             const float *acc = g.gacc + i * (int64_t)AF;
             const float4 a0 = *reinterpret_cast<const float4 *>(acc);
@@ -312,7 +349,7 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
                 for (int c = 0; c < 3; c++) vc[c] = vcol[c] * (1.0f - (float)g.clamped[3 * i + c]);
                 const float X = dxn, Y = dyn, Z = dzn;
                 const float x2 = X * X, y2 = Y * Y, z2 = Z * Z, xy = X * Y, xz = X * Z, yz = Y * Z;
-                const float *sh = shs + i * (int64_t)row;
+                const float *sh = vsh;  // staged coefficients (read fully before the row is overwritten below)
                 float vdir[3] = {0.f, 0.f, 0.f};
                 float basis[16];
                 basis[0] = SH0;
@@ -360,11 +397,10 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
                 for (int k = 0; k < 16; k++) {  // constant trip count keeps basis[] in registers
                     if (k < k_used) {
 #pragma unroll
-                        for (int c = 0; c < 3; c++) put<ACC>(vsh + 3 * k + c, basis[k] * vc[c]);
+                        for (int c = 0; c < 3; c++) vsh[3 * k + c] = basis[k] * vc[c];
                     }
                 }
-                if (!ACC)
-                    for (int e = 3 * k_used; e < row; e++) vsh[e] = 0.f;  // rows k+1..K stay zero (Appendix A.5)
+                for (int e = 3 * k_used; e < row; e++) vsh[e] = 0.f;  // rows k+1..K stay zero (Appendix A.5)
                 const float inv_s = 1.0f / sqrtf(s2 * s2 * s2);
                 vmean[0] += ((s2 - d0 * d0) * vdir[0] - d1 * d0 * vdir[1] - d2 * d0 * vdir[2]) * inv_s;
                 vmean[1] += (-d0 * d1 * vdir[0] + (s2 - d1 * d1) * vdir[1] - d2 * d1 * vdir[2]) * inv_s;
@@ -383,9 +419,38 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
         }
     }
 
+    // coalesced write-out of the CTA's SH-gradient span
+    __syncthreads();
+    {
+        float *dst = vshs + block0 * row;
+        const int64_t nq = aligned16 ? (span >> 2) : 0;
+        for (int64_t q = tid; q < nq; q += BG_THREADS) {
+            const int e = (int)(q << 2);
+            const int gq = e / row, rq = e - gq * row;
+            float vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int gg = gq, rr = rq + u;
+                if (rr >= row) { rr -= row; gg += 1; }
+                vv[u] = s_sh[gg * sh_stride + rr];
+            }
+            float4 *d4 = reinterpret_cast<float4 *>(dst) + q;
+            if (ACC) {
+                const float4 o = *d4;
+                *d4 = make_float4(o.x + vv[0], o.y + vv[1], o.z + vv[2], o.w + vv[3]);
+            } else {
+                *d4 = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            }
+        }
+        for (int64_t e = (nq << 2) + tid; e < span; e += BG_THREADS) {
+            const int gg = (int)(e / row), rr = (int)(e - (int64_t)gg * row);
+            put<ACC>(dst + e, s_sh[gg * sh_stride + rr]);
+        }
+    }
+
     if (pose) {  // CTA-level reduction of the 12 pose cotangents before one atomic each (TODO at projection.jl:242)
         __shared__ float s_pose[BG_THREADS / 32][12];
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
         for (int k = 0; k < 12; k++) {
             float v = pose_acc[k];
@@ -469,12 +534,17 @@ void launch_backward_gaussians(const DevCamera &cam, int64_t n, int sh_degree, i
                                float *vrot, float *vR, float *vt, int accumulate, cudaStream_t s) {
     if (n <= 0) return;
     const unsigned blocks = (unsigned)((n + BG_THREADS - 1) / BG_THREADS);
+    int stride = 3 * K;
+    if ((stride & 1) == 0) stride += 1;
+    const size_t smem = (size_t)BG_THREADS * stride * sizeof(float);
     if (accumulate)
-        backward_gaussians_kernel<true><<<blocks, BG_THREADS, 0, s>>>(cam, n, sh_degree, K, channels, means, shs, opac, scales,
-                                                                     rots, g, vmeans, vshs, vopac, vscales, vrot, vR, vt);
+        backward_gaussians_kernel<true><<<blocks, BG_THREADS, smem, s>>>(cam, n, sh_degree, K, channels, means, shs, opac,
+                                                                        scales, rots, g, vmeans, vshs, vopac, vscales,
+                                                                        vrot, vR, vt, stride);
     else
-        backward_gaussians_kernel<false><<<blocks, BG_THREADS, 0, s>>>(cam, n, sh_degree, K, channels, means, shs, opac, scales,
-                                                                      rots, g, vmeans, vshs, vopac, vscales, vrot, vR, vt);
+        backward_gaussians_kernel<false><<<blocks, BG_THREADS, smem, s>>>(cam, n, sh_degree, K, channels, means, shs, opac,
+                                                                         scales, rots, g, vmeans, vshs, vopac, vscales,
+                                                                         vrot, vR, vt, stride);
     count_launch();
 }
 

@@ -200,15 +200,30 @@ hist_kernel(const uint64_t *__restrict__ keys, const int64_t m, const int depth_
     const int lane = threadIdx.x & 31;
     for (int k = threadIdx.x; k < passes * 256; k += blockDim.x) sh[k] = 0;
     __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t m_round = ((m + 31) / 32) * 32;  // keep warps converged for match_any
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m_round; i += stride) {
-        const bool valid = i < m;
-        const uint64_t ck = valid ? compact_key(keys[i], depth_bits, depth_base) : 0;
-        for (int p = 0; p < passes; p++) {
-            const uint32_t d = valid ? (uint32_t)((ck >> (8 * p)) & 255u) : 0xffffffffu;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);  // warp-aggregated: tile digits cluster
-            if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p * 256 + d], (uint32_t)__popc(peers));
+    // each warp takes 128 consecutive keys per iteration (4 per lane, 128-bit loads): 4 independent chains of
+    // match/atomic per lane hide the match latency; warps stay converged for match_any
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp_global * 128; base < m; base += n_warps * 128) {
+        uint64_t k4[4];
+        const int64_t i0 = base + lane * 4;
+        if (i0 + 3 < m) {
+            const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(keys + i0);
+            const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(keys + i0 + 2);
+            k4[0] = a.x; k4[1] = a.y; k4[2] = b.x; k4[3] = b.y;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++) k4[u] = (i0 + u < m) ? keys[i0 + u] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool valid = i0 + u < m;
+            const uint64_t ck = compact_key(k4[u], depth_bits, depth_base);
+            for (int p = 0; p < passes; p++) {
+                const uint32_t d = valid ? (uint32_t)((ck >> (8 * p)) & 255u) : 0xffffffffu;
+                const unsigned peers = __match_any_sync(0xffffffffu, d);  // warp-aggregated: tile digits cluster
+                if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p * 256 + d], (uint32_t)__popc(peers));
+            }
         }
     }
     __syncthreads();
@@ -288,11 +303,20 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
         atomicExch(my_status, ST_INC | count);
     } else {
         atomicExch(my_status, ST_AGG | count);
-        for (int64_t t = tile - 1; t >= 0; --t) {
-            uint32_t s;
-            do { s = ld_volatile_u32(status + t * 256 + tid); } while ((s >> 30) == 0);
-            tiles_prefix += s & ST_MASK;
-            if ((s >> 30) == 2) break;
+        // chained look-back, 4 predecessors per round trip (independent loads in flight)
+        bool found = false;
+        for (int64_t t = tile - 1; t >= 0 && !found; t -= 4) {
+            uint32_t sv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) sv[j] = (t - j >= 0) ? ld_volatile_u32(status + (t - j) * 256 + tid) : ST_INC;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (found) break;
+                uint32_t sj = sv[j];
+                while ((sj >> 30) == 0) sj = ld_volatile_u32(status + (t - j) * 256 + tid);
+                tiles_prefix += sj & ST_MASK;
+                found = (sj >> 30) == 2;
+            }
         }
         atomicExch(my_status, ST_INC | (tiles_prefix + count));
     }

@@ -16,7 +16,8 @@ import torch
 from oracle.oracle import Oracle, OracleCamera
 from gsrast import Camera, GaussianRasterizer
 
-AMBIG_REL = 2e-5
+AMBIG_REL = 2e-5        # math_mode="reference": sigma is bit-identical to the oracle, only exp() differs by ulps
+AMBIG_REL_FAST = 2e-4   # math_mode="fast": contracted / prescaled sigma differs by ~1e-5 absolute near the thresholds
 IMG_ATOL = 1e-5
 GRAD_RTOL = 1e-4
 CH = {"rgb": 3, "rgbd": 5, "rgbdn": 8}
@@ -162,7 +163,8 @@ def run_case(sc, mode, math_mode="reference", background=(0, 0, 0), R=None, t=No
     img = gpu_forward(rast, dev, cam, sc.sh_degree, background)
     o = oracle()
     ref_img, st = o.forward(sc.means, sc.shs, sc.opacities, sc.scales, sc.rotations, ocam, mode=mode,
-                            sh_degree=sc.sh_degree, background=background, near=near, far=far, ambig_rel=AMBIG_REL)
+                            sh_degree=sc.sh_degree, background=background, near=near, far=far,
+                            ambig_rel=AMBIG_REL if math_mode == "reference" else AMBIG_REL_FAST)
     assert_forward_state_bit_exact(rast, st, sc.n)
     res = {}
     if st.n_rendered:
