@@ -127,11 +127,27 @@ scan_kernel(const int64_t n, const int32_t *__restrict__ in, int32_t *__restrict
 // ----------------------------------------------------------------------------------------------------------
 constexpr int DUP_THREADS = 256;
 constexpr int DUP_SERIAL_MAX = 12;
+constexpr int SORT_MAX_PASSES = 8;
+
+// Digit histograms of the radix sort are accumulated while the keys are generated (no extra pass over the M
+// keys): each thread emits ITS Gaussian's instances, so concurrent shared-memory atomics hit unrelated tiles
+// (low conflict); digits that lie entirely inside the depth bits are added once per Gaussian with weight cnt.
+__device__ __forceinline__ void hist_add_instance(uint32_t *sh, uint64_t ck, int first_pass, int passes) {
+    for (int p = first_pass; p < passes; p++) atomicAdd(&sh[p * 256 + (uint32_t)((ck >> (8 * p)) & 255u)], 1u);
+}
 
 __global__ void __launch_bounds__(DUP_THREADS)
 duplicate_kernel(const int64_t n, const int32_t grid_x, const int32_t grid_y, const int32_t *__restrict__ radii,
                  const float2 *__restrict__ means2d, const float *__restrict__ depths,
-                 const int32_t *__restrict__ offsets, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                 const int32_t *__restrict__ offsets, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                 const int depth_bits, const uint32_t depth_base, const int passes, uint32_t *__restrict__ ghist) {
+    __shared__ uint32_t sh[SORT_MAX_PASSES * 256];
+    const bool do_hist = ghist != nullptr;
+    if (do_hist) {
+        for (int k = threadIdx.x; k < passes * 256; k += DUP_THREADS) sh[k] = 0;
+        __syncthreads();
+    }
+    const int depth_only = depth_bits / 8;  // passes whose 8-bit digit lies entirely in the depth bits
     const int64_t i = (int64_t)blockIdx.x * DUP_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
@@ -149,12 +165,18 @@ duplicate_kernel(const int64_t n, const int32_t grid_x, const int32_t grid_y, co
         }
     }
     const uint32_t id = (uint32_t)(i + 1);  // 1-based, as the reference emits
+    const uint32_t dlow = dbits - depth_base;
+    const int first_pass = depth_only < passes ? depth_only : passes;
+    if (do_hist && cnt > 0)
+        for (int p = 0; p < first_pass; p++) atomicAdd(&sh[p * 256 + ((dlow >> (8 * p)) & 255u)], (uint32_t)cnt);
     if (cnt > 0 && cnt <= DUP_SERIAL_MAX) {
         int64_t o = off;
         for (int32_t y = y0; y < y1; y++)
             for (int32_t x = x0; x < x1; x++) {
-                keys[o] = ((uint64_t)((uint64_t)y * (uint64_t)grid_x + (uint64_t)x) << 32) | dbits;
+                const uint64_t tile = (uint64_t)y * (uint64_t)grid_x + (uint64_t)x;
+                keys[o] = (tile << 32) | dbits;
                 vals[o] = id;
+                if (do_hist) hist_add_instance(sh, (tile << depth_bits) | dlow, first_pass, passes);
                 o++;
             }
     }
@@ -170,11 +192,31 @@ duplicate_kernel(const int64_t n, const int32_t grid_x, const int32_t grid_y, co
         const uint32_t bd = __shfl_sync(0xffffffffu, dbits, src), bid = __shfl_sync(0xffffffffu, id, src);
         const int64_t boff = __shfl_sync(0xffffffffu, off, src);
         const int w = bx1 - bx0;
-        for (int t = lane; t < bcnt; t += 32) {
-            const int ty = by0 + t / w, tx = bx0 + t % w;
-            keys[boff + t] = ((uint64_t)((uint64_t)ty * (uint64_t)grid_x + (uint64_t)tx) << 32) | bd;
-            vals[boff + t] = bid;
+        const uint32_t bdlow = bd - depth_base;
+        for (int t0 = 0; t0 < bcnt; t0 += 32) {  // warp-uniform trip count: match_any below needs convergence
+            const int t = t0 + lane;
+            const bool valid = t < bcnt;
+            uint64_t tile = 0;
+            if (valid) {
+                const int ty = by0 + t / w, tx = bx0 + t % w;
+                tile = (uint64_t)ty * (uint64_t)grid_x + (uint64_t)tx;
+                keys[boff + t] = (tile << 32) | bd;
+                vals[boff + t] = bid;
+            }
+            if (do_hist) {  // neighbouring tiles share their high digits: aggregate within the warp
+                const uint64_t ck = (tile << depth_bits) | bdlow;
+                for (int p = first_pass; p < passes; p++) {
+                    const uint32_t d = valid ? (uint32_t)((ck >> (8 * p)) & 255u) : 0xffffffffu;
+                    const unsigned peers = __match_any_sync(0xffffffffu, d);
+                    if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p * 256 + d], (uint32_t)__popc(peers));
+                }
+            }
         }
+    }
+    if (do_hist) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < passes * 256; k += DUP_THREADS)
+            if (sh[k]) atomicAdd(&ghist[k], sh[k]);
     }
 }
 
@@ -185,7 +227,6 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_IPT = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 keys per CTA
-constexpr int SORT_MAX_PASSES = 8;
 constexpr uint32_t ST_AGG = 1u << 30, ST_INC = 2u << 30, ST_MASK = (1u << 30) - 1;
 
 __device__ __forceinline__ uint64_t compact_key(uint64_t key, int depth_bits, uint32_t depth_base) {
@@ -405,11 +446,12 @@ void launch_scan_tiles(int64_t n, const int32_t *tiles_touched, int32_t *points_
 }
 
 void launch_duplicate(const DevCamera &cam, int64_t n, const GeomPtrs &g, uint64_t *keys, uint32_t *vals,
-                      cudaStream_t s) {
+                      const SortPlan &plan, uint32_t *ghist, cudaStream_t s) {
     if (n <= 0) return;
     const int64_t blocks = (n + DUP_THREADS - 1) / DUP_THREADS;
     duplicate_kernel<<<(unsigned)blocks, DUP_THREADS, 0, s>>>(n, cam.grid_x, cam.grid_y, g.radii, g.means2d, g.depths,
-                                                             g.points_offset, keys, vals);
+                                                             g.points_offset, keys, vals, plan.depth_bits,
+                                                             plan.depth_base, plan.passes, ghist);
     count_launch();
 }
 
@@ -437,9 +479,15 @@ size_t sort_temp_words(int64_t m, const SortPlan &plan) {  // in 32-bit words
            SORT_MAX_PASSES /* tile counters */;
 }
 
+uint32_t *sort_prepare(const SortPlan &plan, int64_t m, uint32_t *temp_words, cudaStream_t s) {
+    // zero {digit histograms, look-back status, tile counters}; returns the histogram buffer [passes][256]
+    cudaMemsetAsync(temp_words, 0, sort_temp_words(m, plan) * sizeof(uint32_t), s);
+    return temp_words;
+}
+
 void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in, const uint32_t *vals_in,
                        uint64_t *keys_out, uint32_t *vals_out, uint64_t *keys_tmp, uint32_t *vals_tmp,
-                       uint32_t *temp_words, cudaStream_t s) {
+                       uint32_t *temp_words, bool hist_ready, cudaStream_t s) {
     if (m <= 0) return;
     static bool attr_set = false;
     if (!attr_set) {
@@ -447,14 +495,15 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
         attr_set = true;
     }
     const size_t tiles = (size_t)((m + SORT_TILE - 1) / SORT_TILE);
-    cudaMemsetAsync(temp_words, 0, sort_temp_words(m, plan) * sizeof(uint32_t), s);
     uint32_t *ghist = temp_words;
     uint32_t *status = ghist + (size_t)plan.passes * 256;
     uint32_t *counters = status + (size_t)plan.passes * tiles * 256;
-    int hb = (int)((m + 256 * 16 - 1) / (256 * 16));
-    if (hb > 148 * 8) hb = 148 * 8;
-    hist_kernel<<<hb, 256, 0, s>>>(keys_in, m, plan.depth_bits, plan.depth_base, plan.passes, ghist);
-    count_launch();
+    if (!hist_ready) {
+        int hb = (int)((m + 256 * 16 - 1) / (256 * 16));
+        if (hb > 148 * 8) hb = 148 * 8;
+        hist_kernel<<<hb, 256, 0, s>>>(keys_in, m, plan.depth_bits, plan.depth_base, plan.passes, ghist);
+        count_launch();
+    }
     const uint64_t *ksrc = keys_in;
     const uint32_t *vsrc = vals_in;
     for (int p = 0; p < plan.passes; p++) {

@@ -57,19 +57,21 @@ void launch_scan_tiles(int64_t n, const int32_t *tiles_touched, int32_t *points_
                        int64_t *total_dev, cudaStream_t s);
 size_t scan_state_words(int64_t n);
 
-void launch_duplicate(const DevCamera &cam, int64_t n, const GeomPtrs &g, uint64_t *keys, uint32_t *vals,
-                      cudaStream_t s);
-
 struct SortPlan {
     int tile_bits, depth_bits, passes;
     uint32_t depth_base;
 };
+// ghist != nullptr: also accumulate the radix-sort digit histograms [passes][256] (zeroed by sort_prepare)
+void launch_duplicate(const DevCamera &cam, int64_t n, const GeomPtrs &g, uint64_t *keys, uint32_t *vals,
+                      const SortPlan &plan, uint32_t *ghist, cudaStream_t s);
 SortPlan make_sort_plan(int64_t n_tiles, float near_plane, float far_plane);
 size_t sort_temp_words(int64_t m, const SortPlan &plan);
 // keys_in/vals_in are left intact; result lands in keys_out/vals_out; (keys_tmp, vals_tmp) is scratch of size m.
+uint32_t *sort_prepare(const SortPlan &plan, int64_t m, uint32_t *temp_words, cudaStream_t s);
+// hist_ready: the digit histograms were already accumulated into sort_prepare()'s buffer (by launch_duplicate)
 void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in, const uint32_t *vals_in,
                        uint64_t *keys_out, uint32_t *vals_out, uint64_t *keys_tmp, uint32_t *vals_tmp,
-                       uint32_t *temp_words, cudaStream_t s);
+                       uint32_t *temp_words, bool hist_ready, cudaStream_t s);
 
 void launch_tile_ranges(int64_t m, const uint64_t *keys_sorted, uint32_t *ranges, cudaStream_t s);
 

@@ -386,12 +386,13 @@ int gsr_forward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree
 
     {
         StageTimer tm(h, s, GSR_STAGE_DUPLICATE);
-        launch_duplicate(dc, n, h->g, h->keys_unsorted, h->vals_unsorted, s);
+        uint32_t *ghist = sort_prepare(h->plan, m, h->sort_temp, s);
+        launch_duplicate(dc, n, h->g, h->keys_unsorted, h->vals_unsorted, h->plan, ghist, s);
     }
     {
         StageTimer tm(h, s, GSR_STAGE_SORT);
         launch_sort_pairs(h->plan, m, h->keys_unsorted, h->vals_unsorted, h->keys_sorted, h->vals_sorted, h->keys_tmp,
-                          h->vals_tmp, h->sort_temp, s);
+                          h->vals_tmp, h->sort_temp, /*hist_ready=*/true, s);
     }
     {
         StageTimer tm(h, s, GSR_STAGE_RANGES);
@@ -547,8 +548,9 @@ int gsr_sort_pairs(GsrHandle *h, const uint64_t *keys_in_dev, const uint32_t *va
         return fail(h, GSR_EINVAL, "gsr_sort_pairs: null argument");
     int rc = ensure_binning(h, m);
     if (rc) return rc;
+    sort_prepare(h->plan, m, h->sort_temp, static_cast<cudaStream_t>(stream));
     launch_sort_pairs(h->plan, m, keys_in_dev, vals_in_dev, keys_out_dev, vals_out_dev, h->keys_tmp, h->vals_tmp,
-                      h->sort_temp, static_cast<cudaStream_t>(stream));
+                      h->sort_temp, /*hist_ready=*/false, static_cast<cudaStream_t>(stream));
     CK(cudaGetLastError());
     return GSR_OK;
 }

@@ -133,7 +133,7 @@ def assert_grads_close(g, ref, rtol=GRAD_RTOL, keys=("vmeans", "vshs", "vopaciti
     """||Δ||∞ / ||ref||∞ <= 1e-4 per tensor.  Gaussians flagged by the oracle as owning a pair within AMBIG_REL of a
     branch threshold (`ambig_g`) gain or lose that pair's whole contribution when the branch flips, so they are
     held to `ambig_rtol` instead (and counted)."""
-    out = {}
+    out, errors = {}, []
     keep = None if ambig_g is None else (np.asarray(ambig_g) == 0)
     for k in keys:
         a = np_(g[k]).reshape(ref[k].shape) if isinstance(g[k], torch.Tensor) else g[k]
@@ -145,10 +145,15 @@ def assert_grads_close(g, ref, rtol=GRAD_RTOL, keys=("vmeans", "vshs", "vopaciti
         else:
             out[k] = float(d[keep].max()) if keep.any() else 0.0
             worst_amb = float(d[~keep].max()) if (~keep).any() else 0.0
-            assert worst_amb <= ambig_rtol, f"{k}: ambiguous-Gaussian error {worst_amb:.3e} > {ambig_rtol:g}"
-        assert out[k] <= rtol, f"{k}: relative error {out[k]:.3e} > {rtol:g}"
+            out[k + "_ambiguous"] = worst_amb
+            if worst_amb > ambig_rtol:
+                errors.append(f"{k}: ambiguous-Gaussian error {worst_amb:.3e} > {ambig_rtol:g}")
+        if out[k] > rtol:
+            worst = int(np.argmax(np.where(keep, d, 0) if keep is not None else d))
+            errors.append(f"{k}: relative error {out[k]:.3e} > {rtol:g} (row {worst})")
     if keep is not None:
         out["ambiguous_gaussians"] = int((~keep).sum())
+    assert not errors, "; ".join(errors) + f" | all: {out}"
     return out
 
 
