@@ -215,20 +215,16 @@ def main():
     vpix = vpix_h.to(dev, non_blocking=True)
     rast = GaussianRasterizer(width=W, height=H, mode=mode, math_mode=args.math, device=dev)
 
-    # one flat gradient table (59 floats / Gaussian at K=16): vrot first keeps its 16-byte alignment
-    sizes = [("vrot", 4), ("vmeans", 3), ("vscales", 3), ("vopacities", 1), ("vshs", 3 * K)]
-    flat = torch.zeros(n * sum(s for _, s in sizes), device=dev)
-    outs, off = {}, 0
-    for name, s in sizes:
-        outs[name] = flat[off:off + n * s].view((n, K, 3) if name == "vshs" else (n, s))
-        off += n * s
+    # one flat gradient table (59 floats / Gaussian at K=16) so that the cross-GPU reduction is one collective
+    from gsrast.distributed import GradientTable, allreduce_gradients_
+    table = GradientTable(n, K, dev)
+    flat, outs = table.flat, table.outs()
 
     def step():
         rast._forward(d["means"], d["shs"], d["opac"], d["scales"], d["rots"], None, None, cam, deg, (0, 0, 0), None, None)
         rast._backward(vpix, d["means"], d["shs"], d["opac"], d["scales"], d["rots"], None, None, cam, deg, (0, 0, 0),
                        outs=dict(outs))
-        if world > 1:
-            dist.all_reduce(flat)
+        allreduce_gradients_(table)
 
     def barrier():
         torch.cuda.synchronize()
@@ -280,7 +276,7 @@ def main():
                                     (0, 0, 0), None, None)
                 rast._backward(vp, dd["means"], dd["shs"], dd["opac"], dd["scales"], dd["rots"], None, None, cam, deg,
                                (0, 0, 0), outs=dict(outs))
-                dist.all_reduce(flat)
+                allreduce_gradients_(table)
                 out_h["image"].copy_(img, non_blocking=True)
                 flat_h.copy_(flat, non_blocking=True)
                 torch.cuda.synchronize()
