@@ -331,9 +331,15 @@ def main():
         gbs = bts[name] / (msv * 1e-3) / 1e9 if msv > 0 else None
         stages[name] = {"ms": round(msv, 4), "alg_bytes": int(bts[name]), "gbs": None if gbs is None else round(gbs, 1),
                         "hbm_frac": None if gbs is None else round(gbs / hbm_peak, 4)}
+    traffic = {}
+    try:  # DRAM bytes per launch from the committed ncu capture (profiles/), same workload
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["per_launch_bytes"]
+    except Exception:
+        pass
     dominant = max(acc, key=lambda k2: acc[k2])
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": stages[dominant]["gbs"], "peak": hbm_peak,
-                "unit": "GB/s", "frac": stages[dominant]["hbm_frac"], "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": stages[dominant]["hbm_frac"], "traffic": traffic.get(dominant), "peak_source": peak_src,
+                "traffic_source": "profiles/ncu_traffic.json (ncu dram bytes per launch)" if dominant in traffic else None,
                 "ms": stages[dominant]["ms"], "share_of_step": round(acc[dominant] / sum(acc.values()), 3),
                 "note": "the compositing kernels are FP32/SFU-bound, not HBM-bound (SURVEY.md §8d): see roofline_fp32"}
     step_bytes = sum(bts.values())

@@ -157,6 +157,31 @@ def assert_grads_close(g, ref, rtol=GRAD_RTOL, keys=("vmeans", "vshs", "vopaciti
     return out
 
 
+def assert_grads_as_accurate_as_reference(g, ref32, ref64, rtol=GRAD_RTOL,
+                                           keys=("vmeans", "vshs", "vopacities", "vscales", "vrot")):
+    """Full-size criterion for math_mode="fast".  At 1M Gaussians the reference's own fp32 arithmetic is up to ~8e-4
+    (of each tensor's max) away from an fp64 evaluation of the same formulas: (1-alpha) loses 2 digits for
+    near-opaque Gaussians, T is a product of hundreds of such factors, and the T'<1e-4 termination flips on
+    thousands of pixels between fp32 and fp64.  A different-but-valid fp32 evaluation order cannot match the fp32
+    oracle better than that noise, so the fast path is required to be AS ACCURATE AS THE REFERENCE ARITHMETIC:
+    per Gaussian, err(gpu, fp64) <= rtol + err(fp32 oracle, fp64), errors relative to the tensor's max."""
+    out, errors = {}, []
+    for k in keys:
+        a = np_(g[k]).reshape(ref64[k].shape).astype(np.float64)
+        assert np.isfinite(a).all(), f"{k} has non-finite values"
+        scale = max(float(np.abs(ref64[k]).max()), 1e-30)
+        rows = a.shape[0]
+        d_gpu = np.abs(a - ref64[k]).reshape(rows, -1).max(1) / scale
+        d_ref = np.abs(ref32[k].astype(np.float64) - ref64[k]).reshape(rows, -1).max(1) / scale
+        excess = d_gpu - d_ref
+        out[k] = dict(gpu_vs_fp64=float(d_gpu.max()), fp32ref_vs_fp64=float(d_ref.max()), excess=float(excess.max()),
+                      closer_than_reference=float((d_gpu <= d_ref).mean()))
+        if excess.max() > rtol:
+            errors.append(f"{k}: row {int(np.argmax(excess))} exceeds the reference's own fp32 error by {excess.max():.3e}")
+    assert not errors, "; ".join(errors) + f" | all: {out}"
+    return out
+
+
 def run_case(sc, mode, math_mode="reference", background=(0, 0, 0), R=None, t=None, principal=(0.5, 0.5),
              check_backward=True, near=0.2, far=1000.0, vpix_seed=1, grad_rtol=GRAD_RTOL):
     """Full forward(+backward) parity of one scene; returns a dict of measured errors."""
