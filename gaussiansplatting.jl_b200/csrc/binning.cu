@@ -15,6 +15,7 @@
 // The published buffers hold the canonical (tile << 32 | bits(depth)) keys and 1-based ids.
 //
 // All integer work: bit-exact by construction; compiled with default flags.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -225,8 +226,8 @@ duplicate_kernel(const int64_t n, const int32_t grid_x, const int32_t grid_y, co
 // ----------------------------------------------------------------------------------------------------------
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_IPT = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 keys per CTA
+// keys per thread (template parameter of the pass kernel): 8 -> 2048-key tiles, ~50 registers, 34 KB smem
+// (5 CTAs/SM); 16 -> 4096-key tiles, 80 registers, 59 KB (3 CTAs/SM).  The pass is latency-bound, so occupancy wins.
 constexpr uint32_t ST_AGG = 1u << 30, ST_INC = 2u << 30, ST_MASK = (1u << 30) - 1;
 
 __device__ __forceinline__ uint64_t compact_key(uint64_t key, int depth_bits, uint32_t depth_base) {
@@ -272,9 +273,10 @@ hist_kernel(const uint64_t *__restrict__ keys, const int64_t m, const int depth_
         if (sh[k]) atomicAdd(&ghist[k], sh[k]);
 }
 
+template <int SORT_IPT>
 struct SortSmem {
-    uint64_t keys[SORT_TILE];
-    uint32_t vals[SORT_TILE];
+    uint64_t keys[SORT_THREADS * SORT_IPT];
+    uint32_t vals[SORT_THREADS * SORT_IPT];
     uint32_t whist[SORT_WARPS][256];
     uint32_t excl[256];
     uint32_t gbase[256];
@@ -283,13 +285,15 @@ struct SortSmem {
     uint32_t tile;
 };
 
+template <int SORT_IPT>
 __global__ void __launch_bounds__(SORT_THREADS)
 onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, const int64_t m, const int shift,
                 const int depth_bits, const uint32_t depth_base, const uint32_t *__restrict__ ghist /* [256] */,
                 uint32_t *status /* [tiles][256] */, uint32_t *tile_counter) {
+    constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortSmem &S = *reinterpret_cast<SortSmem *>(smem_raw);
+    SortSmem<SORT_IPT> &S = *reinterpret_cast<SortSmem<SORT_IPT> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) S.tile = atomicAdd(tile_counter, 1u);
 #pragma unroll
@@ -338,29 +342,9 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
         S.whist[w][tid] = count;
         count += c;
     }
+    // publish this tile's per-digit count right away (aggregate), so successors can start summing
     uint32_t *my_status = status + tile * 256 + tid;
-    uint32_t tiles_prefix = 0;
-    if (tile == 0) {
-        atomicExch(my_status, ST_INC | count);
-    } else {
-        atomicExch(my_status, ST_AGG | count);
-        // chained look-back, 4 predecessors per round trip (independent loads in flight)
-        bool found = false;
-        for (int64_t t = tile - 1; t >= 0 && !found; t -= 4) {
-            uint32_t sv[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) sv[j] = (t - j >= 0) ? ld_volatile_u32(status + (t - j) * 256 + tid) : ST_INC;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (found) break;
-                uint32_t sj = sv[j];
-                while ((sj >> 30) == 0) sj = ld_volatile_u32(status + (t - j) * 256 + tid);
-                tiles_prefix += sj & ST_MASK;
-                found = (sj >> 30) == 2;
-            }
-        }
-        atomicExch(my_status, ST_INC | (tiles_prefix + count));
-    }
+    atomicExch(my_status, (tile == 0 ? ST_INC : ST_AGG) | count);
     // two CTA-wide exclusive scans over the 256 digits: this tile's counts and the global histogram
     const uint32_t gh = ghist[tid];
     uint32_t inc1 = count, inc2 = gh;
@@ -378,10 +362,9 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
     const uint32_t excl = off1 + inc1 - count;
     const uint32_t gexcl = off2 + inc2 - gh;
     S.excl[tid] = excl;
-    S.gbase[tid] = gexcl + tiles_prefix - excl;  // global position = gbase[d] + local sorted position
     __syncthreads();
 
-    // ---- scatter into shared memory in digit order, then stream out runs ----------------------------------
+    // ---- scatter into shared memory in digit order (needs only CTA-local offsets) --------------------------
 #pragma unroll
     for (int j = 0; j < SORT_IPT; j++) {
         const int local = warp * (32 * SORT_IPT) + j * 32 + lane;
@@ -392,7 +375,31 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
             S.vals[pos] = val[j];
         }
     }
+
+    // ---- chained look-back over the preceding tiles, per digit; done AFTER the local scatter so that the
+    //      predecessors have had time to publish (4 predecessors per round trip, independent loads in flight)
+    uint32_t tiles_prefix = 0;
+    if (tile > 0) {
+        bool found = false;
+        for (int64_t t = tile - 1; t >= 0 && !found; t -= 4) {
+            uint32_t sv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) sv[j] = (t - j >= 0) ? ld_volatile_u32(status + (t - j) * 256 + tid) : ST_INC;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (found) break;
+                uint32_t sj = sv[j];
+                while ((sj >> 30) == 0) sj = ld_volatile_u32(status + (t - j) * 256 + tid);
+                tiles_prefix += sj & ST_MASK;
+                found = (sj >> 30) == 2;
+            }
+        }
+        atomicExch(my_status, ST_INC | (tiles_prefix + count));
+    }
+    S.gbase[tid] = gexcl + tiles_prefix - excl;  // global position = gbase[d] + local sorted position
     __syncthreads();
+
+    // ---- stream out the digit runs ------------------------------------------------------------------------
     for (int p = tid; p < cnt; p += SORT_THREADS) {
         const uint64_t k = S.keys[p];
         const uint32_t d = (uint32_t)((compact_key(k, depth_bits, depth_base) >> shift) & 255u);
@@ -473,8 +480,18 @@ SortPlan make_sort_plan(int64_t n_tiles, float near_plane, float far_plane) {
     return p;
 }
 
+int sort_ipt() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("GSR_SORT_IPT");
+        v = (e && atoi(e) == 8) ? 8 : 16;
+    }
+    return v;
+}
+static int64_t sort_tile_keys() { return (int64_t)SORT_THREADS * sort_ipt(); }
+
 size_t sort_temp_words(int64_t m, const SortPlan &plan) {  // in 32-bit words
-    const size_t tiles = (size_t)((m + SORT_TILE - 1) / SORT_TILE);
+    const size_t tiles = (size_t)((m + sort_tile_keys() - 1) / sort_tile_keys());
     return (size_t)plan.passes * 256 /* ghist */ + (size_t)plan.passes * tiles * 256 /* status */ +
            SORT_MAX_PASSES /* tile counters */;
 }
@@ -491,10 +508,12 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
     if (m <= 0) return;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+        cudaFuncSetAttribute(onesweep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<8>));
+        cudaFuncSetAttribute(onesweep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<16>));
         attr_set = true;
     }
-    const size_t tiles = (size_t)((m + SORT_TILE - 1) / SORT_TILE);
+    const int ipt = sort_ipt();
+    const size_t tiles = (size_t)((m + sort_tile_keys() - 1) / sort_tile_keys());
     uint32_t *ghist = temp_words;
     uint32_t *status = ghist + (size_t)plan.passes * 256;
     uint32_t *counters = status + (size_t)plan.passes * tiles * 256;
@@ -511,9 +530,14 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
         const bool to_out = ((plan.passes - 1 - p) % 2) == 0;
         uint64_t *kdst = to_out ? keys_out : keys_tmp;
         uint32_t *vdst = to_out ? vals_out : vals_tmp;
-        onesweep_kernel<<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem), s>>>(
-            ksrc, vsrc, kdst, vdst, m, 8 * p, plan.depth_bits, plan.depth_base, ghist + (size_t)p * 256,
-            status + (size_t)p * tiles * 256, counters + p);
+        if (ipt == 16)
+            onesweep_kernel<16><<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem<16>), s>>>(
+                ksrc, vsrc, kdst, vdst, m, 8 * p, plan.depth_bits, plan.depth_base, ghist + (size_t)p * 256,
+                status + (size_t)p * tiles * 256, counters + p);
+        else
+            onesweep_kernel<8><<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem<8>), s>>>(
+                ksrc, vsrc, kdst, vdst, m, 8 * p, plan.depth_bits, plan.depth_base, ghist + (size_t)p * 256,
+                status + (size_t)p * tiles * 256, counters + p);
         count_launch();
         ksrc = kdst;
         vsrc = vdst;
