@@ -205,7 +205,7 @@ def main():
     sc = make_config(args.config)
     C = {"rgb": 3, "rgbd": 5, "rgbdn": 8}[mode]
     K = sc.shs.shape[1]
-    R, t = view_pose(rank, world)
+    R, t = view_pose(rank, world, max_yaw_deg=2.0, max_shift=0.1)  # near-identical work per rank (weak scaling)
     cam = Camera(fx=sc.fx, fy=sc.fy, width=W, height=H, R=R, t=t)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     host = dict(means=pin(sc.means), shs=pin(sc.shs), opac=pin(sc.opacities.reshape(-1, 1)), scales=pin(sc.scales),

@@ -71,13 +71,15 @@ def make_vpixels(width: int, height: int, channels: int, seed: int) -> np.ndarra
     return (rng.normal(0.0, 1.0, (height, width, channels)) / (width * height)).astype(np.float32)
 
 
-def view_pose(view: int, n_views: int = 8):
-    """w2c rotation (3,3) and translation (3,) for view `view`: yaw in ±20°, x-translation in ±1 (config C3)."""
+def view_pose(view: int, n_views: int = 8, max_yaw_deg: float = 20.0, max_shift: float = 1.0):
+    """w2c rotation (3,3) and translation (3,) for view `view`: yaw in ±max_yaw_deg, x-translation in ±max_shift
+    (config C3 uses ±20° / ±1; bench.py's weak-scaling runs use ±2° / ±0.1 so that every rank's view carries
+    the same work as the single-GPU identity view to within a few percent)."""
     if n_views <= 1:
         return np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
     a = -1.0 + 2.0 * view / (n_views - 1)
-    yaw = np.deg2rad(20.0) * a
+    yaw = np.deg2rad(max_yaw_deg) * a
     c, s = np.cos(yaw), np.sin(yaw)
     R = np.array([[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]], np.float32)
-    t = np.array([a, 0.0, 0.0], np.float32)
+    t = np.array([a * max_shift, 0.0, 0.0], np.float32)
     return R, t
