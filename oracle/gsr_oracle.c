@@ -662,12 +662,15 @@ EXPORT void orc_pack_features(int64_t n, int channels, const real *rgbs, const r
  * ambig (optional, per pixel) flags pixels where some pair sits within `ambig_rel` (relative) of one of the
  * kernel's discontinuities (σ<0, α<1/255, T'<1e-4): there a 1-ulp difference in exp() legitimately flips a
  * branch, so parity tests hold those pixels to a looser bound (see tests/parity.py).  ambig_g (optional, per
- * Gaussian) flags the Gaussian of such a pair: its gradient gains or loses that pair's whole contribution. */
+ * Gaussian) flags the Gaussian of such a pair: its gradient gains or loses that pair's whole contribution.
+ * ambig_cond widens the sigma / alpha windows by ambig_cond * (|cb dx dy| + |ca dx^2|/2 + |cc dy^2|/2): a
+ * contracted (FMA) evaluation of sigma differs from this one by a few ulps of its largest term, which for
+ * elongated Gaussians far exceeds ulps of sigma itself (cancellation). */
 EXPORT void orc_render(int channels, int32_t width, int32_t height, const uint32_t *ranges, const uint32_t *values,
                        const real *means2d, const real *opacities, const real *conics, const real *features,
                        const real *background, real *out_color, uint32_t *n_contrib, real *accum_alpha,
                        uint8_t *covis, real *uncert, int64_t *counts, int32_t tile_y0, int32_t tile_y1,
-                       uint8_t *ambig, real ambig_rel, uint8_t *ambig_g) {
+                       uint8_t *ambig, real ambig_rel, uint8_t *ambig_g, real ambig_cond) {
     int32_t gx = (width + BLOCK - 1) / BLOCK, gy = (height + BLOCK - 1) / BLOCK;
     if (tile_y1 <= 0 || tile_y1 > gy) tile_y1 = gy;
     if (tile_y0 < 0) tile_y0 = 0;
@@ -691,10 +694,12 @@ EXPORT void orc_render(int channels, int32_t width, int32_t height, const uint32
                         const real *cn = conics + 3 * (int64_t)g;
                         real sigma = (cn[1] * dx) * dy + RC(0.5) * (cn[0] * (dx * dx) + cn[2] * (dy * dy));
                         ev_total++;
-                        if (ambig && R_FABS(sigma) <= ambig_rel) { ambig[(int64_t)py * width + px] = 1; if (ambig_g) ambig_g[g] = 1; }
+                        real win = ambig_rel;
+                        if (ambig) win += ambig_cond * (R_FABS((cn[1] * dx) * dy) + RC(0.5) * (R_FABS(cn[0] * (dx * dx)) + R_FABS(cn[2] * (dy * dy))));
+                        if (ambig && R_FABS(sigma) <= win) { ambig[(int64_t)py * width + px] = 1; if (ambig_g) ambig_g[g] = 1; }
                         if (sigma < (real)0) continue;
                         real alpha = rmin_(RC(0.99), opacities[g] * R_EXP(-sigma));
-                        if (ambig && R_FABS(alpha * RC(255.0) - RC(1.0)) <= ambig_rel) { ambig[(int64_t)py * width + px] = 1; if (ambig_g) ambig_g[g] = 1; }
+                        if (ambig && R_FABS(alpha * RC(255.0) - RC(1.0)) <= win) { ambig[(int64_t)py * width + px] = 1; if (ambig_g) ambig_g[g] = 1; }
                         if (alpha < RC(1.0) / RC(255.0)) continue;
                         real Tt = T * (RC(1.0) - alpha);
                         if (ambig && R_FABS(Tt * RC(1e4) - RC(1.0)) <= ambig_rel) { ambig[(int64_t)py * width + px] = 1; if (ambig_g) ambig_g[g] = 1; }

@@ -280,13 +280,13 @@ class Oracle:
     # ---------------------------------------------------- rasterize (forward)
     def forward(self, means, shs, opacities, scales, rotations, cam: OracleCamera, *, mode="rgbd", sh_degree=0,
                 background=(0.0, 0.0, 0.0), near=0.2, far=1000.0, covisibilities=None, uncertainties=None,
-                state: OracleState | None = None, tile_rows=None, ambig_rel=None):
+                state: OracleState | None = None, tile_rows=None, ambig_rel=None, ambig_cond=0.0):
         """`rasterize` — rasterizer.jl:255-408.  Returns (image (H,W,C), state).
 
         `state` carries stale per-Gaussian values across calls exactly like `rast.gstate`.
         `tile_rows=(y0,y1)` restricts render! to a band of tile rows (bench sampling only).
         `ambig_rel`: if set, `state.ambiguous` (H,W) flags pixels with a pair within that relative distance
-        of a branch threshold (see orc_render)."""
+        of a branch threshold (see orc_render); `ambig_cond` widens it by the conditioning of sigma."""
         lib, p = self.lib, self.p
         channels = MODES[mode]
         W, H = int(cam.width), int(cam.height)
@@ -350,7 +350,7 @@ class Oracle:
         lib.orc_render(C.c_int(channels), C.c_int32(W), C.c_int32(H), p(st.ranges), p(st.values_sorted),
                        p(st.means2d), p(opacities), p(st.conics), p(feats), p(bg), p(image), p(st.n_contrib),
                        p(st.accum_alpha), p(covisibilities), p(uncertainties), p(st.counts_fwd),
-                       C.c_int32(y0), C.c_int32(y1), p(st.ambiguous), self.r(ambig_rel or 0.0), p(st.ambiguous_g))
+                       C.c_int32(y0), C.c_int32(y1), p(st.ambiguous), self.r(ambig_rel or 0.0), p(st.ambiguous_g), self.r(ambig_cond))
         return image, st
 
     # --------------------------------------------------- ∇rasterize (backward)
