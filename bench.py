@@ -267,8 +267,8 @@ def main():
         flat_h = torch.empty_like(flat, device="cpu").pin_memory() if world > 1 else None
 
         def step_e2e():
-            if world == 1:  # the C-ABI host entry point: H2D, forward, backward, D2H, one sync
-                rast.forward_backward_host(host, vpix_h, cam, deg, out=out_h)
+            if world == 1:  # the C-ABI host entry point, pipelined: step k+1's H2D overlaps step k's compute / D2H
+                rast.forward_backward_host(host, vpix_h, cam, deg, out=out_h, wait=False)
             else:
                 dd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
                 vp = vpix_h.to(dev, non_blocking=True)
@@ -283,11 +283,13 @@ def main():
 
         for _ in range(3):
             step_e2e()
+        rast.host_wait()
         barrier()
         ke = max(5, min(args.steps, 20))
         e0.record()
         for _ in range(ke):
             step_e2e()
+        rast.host_wait()  # every step's D2H has landed in the host buffers
         e1.record()
         barrier()
         mse = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -295,7 +297,8 @@ def main():
             dist.all_reduce(mse, op=dist.ReduceOp.MAX)
         e2e = {"value": world * ke / (float(mse.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(mse.item()) / ke, "steps": ke,
-               "api": "gsr_forward_backward_host (C ABI, pinned host buffers)" if world == 1 else
+               "api": "gsr_forward_backward_host_async + gsr_host_wait (C ABI, pinned host buffers, double-buffered "
+                      "staging: H2D / compute / D2H of consecutive steps overlap)" if world == 1 else
                       "pinned torch copies + gsr_forward/gsr_backward + NCCL all-reduce + D2H"}
 
     if rank != 0:

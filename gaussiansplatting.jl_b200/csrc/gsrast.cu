@@ -59,9 +59,14 @@ struct GsrHandle {
     cudaEvent_t ev[2 * GSR_NUM_STAGES] = {};
     bool ev_used[GSR_NUM_STAGES] = {};
 
-    // staging for the host-buffer entry point
-    DevBuf st_means, st_shs, st_opac, st_scales, st_rots, st_vpix, st_image, st_vmeans, st_vshs, st_vopac, st_vscales,
-        st_vrot;
+    // staging for the host-buffer entry points: two slots so that step k+1's H2D overlaps step k's compute / D2H
+    struct HostSlot {
+        DevBuf means, shs, opac, scales, rots, vpix, image, vmeans, vshs, vopac, vscales, vrot;
+        cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+        bool d2h_pending = false;
+    } slot[2];
+    int next_slot = 0;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
 };
 
 namespace {
@@ -279,10 +284,14 @@ int gsr_release_scene_buffers(GsrHandle *h) {
     if (!h) return GSR_EINVAL;
     free_geometry(h);
     free_binning(h);
-    DevBuf *st[] = {&h->st_means, &h->st_shs, &h->st_opac, &h->st_scales, &h->st_rots, &h->st_vpix,
-                    &h->st_image, &h->st_vmeans, &h->st_vshs, &h->st_vopac, &h->st_vscales, &h->st_vrot};
-    for (DevBuf *b : st)
-        if (b->p) { cudaFree(b->p); h->bytes -= b->bytes; b->p = nullptr; b->bytes = 0; }
+    for (auto &sl : h->slot) {
+        if (sl.d2h_pending && sl.d2h_done) cudaEventSynchronize(sl.d2h_done);
+        sl.d2h_pending = false;
+        DevBuf *st[] = {&sl.means, &sl.shs, &sl.opac, &sl.scales, &sl.rots, &sl.vpix,
+                        &sl.image, &sl.vmeans, &sl.vshs, &sl.vopac, &sl.vscales, &sl.vrot};
+        for (DevBuf *b : st)
+            if (b->p) { cudaFree(b->p); h->bytes -= b->bytes; b->p = nullptr; b->bytes = 0; }
+    }
     h->fwd_valid = false;
     h->last_n = h->last_m = 0;
     return GSR_OK;
@@ -299,6 +308,11 @@ int gsr_destroy(GsrHandle *h) {
     if (h->total_host) cudaFreeHost(h->total_host);
     for (cudaEvent_t e : h->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &sl : h->slot)
+        for (cudaEvent_t e : {sl.h2d_done, sl.compute_done, sl.d2h_done})
+            if (e) cudaEventDestroy(e);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     delete h;
     return GSR_OK;
 }
@@ -460,48 +474,95 @@ int gsr_update_stats(GsrHandle *h, int64_t n, int32_t *max_radii, float *accum_g
     return GSR_OK;
 }
 
-int gsr_forward_backward_host(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K,
-                              const float *means_h, const float *shs_h, const float *opacities_h,
-                              const float *scales_h, const float *rotations_h, const float background[3],
-                              const float *vpixels_h, float *image_h, float *vmeans_h, float *vshs_h,
-                              float *vopacities_h, float *vscales_h, float *vrot_h, int64_t *n_rendered,
-                              void *stream) {
+int gsr_forward_backward_host_async(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K,
+                                    const float *means_h, const float *shs_h, const float *opacities_h,
+                                    const float *scales_h, const float *rotations_h, const float background[3],
+                                    const float *vpixels_h, float *image_h, float *vmeans_h, float *vshs_h,
+                                    float *vopacities_h, float *vscales_h, float *vrot_h, int64_t *n_rendered,
+                                    void *stream) {
     if (!h) return GSR_EINVAL;
     if (!means_h || !shs_h || !opacities_h || !scales_h || !rotations_h || !vpixels_h)
         return fail(h, GSR_EINVAL, "gsr_forward_backward_host: null input");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t f = sizeof(float), N = (size_t)n;
     const size_t img = (size_t)h->cfg.channels * h->cfg.width * h->cfg.height * f;
+    if (!h->h2d_stream) {
+        CK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        for (auto &sl : h->slot) {
+            CK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+        }
+    }
+    GsrHandle::HostSlot &sl = h->slot[h->next_slot];
+    h->next_slot ^= 1;
+    // the slot's previous download (two submissions ago) must have drained before its buffers are reused
+    if (sl.d2h_pending) { CK(cudaEventSynchronize(sl.d2h_done)); sl.d2h_pending = false; }
     int rc;
-    if ((rc = ensure_stage(h, h->st_means, 3 * N * f)) || (rc = ensure_stage(h, h->st_shs, 3 * (size_t)K * N * f)) ||
-        (rc = ensure_stage(h, h->st_opac, N * f)) || (rc = ensure_stage(h, h->st_scales, 3 * N * f)) ||
-        (rc = ensure_stage(h, h->st_rots, 4 * N * f)) || (rc = ensure_stage(h, h->st_vpix, img)) ||
-        (rc = ensure_stage(h, h->st_image, img)) || (rc = ensure_stage(h, h->st_vmeans, 3 * N * f)) ||
-        (rc = ensure_stage(h, h->st_vshs, 3 * (size_t)K * N * f)) || (rc = ensure_stage(h, h->st_vopac, N * f)) ||
-        (rc = ensure_stage(h, h->st_vscales, 3 * N * f)) || (rc = ensure_stage(h, h->st_vrot, 4 * N * f)))
+    if ((rc = ensure_stage(h, sl.means, 3 * N * f)) || (rc = ensure_stage(h, sl.shs, 3 * (size_t)K * N * f)) ||
+        (rc = ensure_stage(h, sl.opac, N * f)) || (rc = ensure_stage(h, sl.scales, 3 * N * f)) ||
+        (rc = ensure_stage(h, sl.rots, 4 * N * f)) || (rc = ensure_stage(h, sl.vpix, img)) ||
+        (rc = ensure_stage(h, sl.image, img)) || (rc = ensure_stage(h, sl.vmeans, 3 * N * f)) ||
+        (rc = ensure_stage(h, sl.vshs, 3 * (size_t)K * N * f)) || (rc = ensure_stage(h, sl.vopac, N * f)) ||
+        (rc = ensure_stage(h, sl.vscales, 3 * N * f)) || (rc = ensure_stage(h, sl.vrot, 4 * N * f)))
         return rc;
-    CK(cudaMemcpyAsync(h->st_means.p, means_h, 3 * N * f, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->st_scales.p, scales_h, 3 * N * f, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->st_rots.p, rotations_h, 4 * N * f, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->st_opac.p, opacities_h, N * f, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->st_shs.p, shs_h, 3 * (size_t)K * N * f, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->st_vpix.p, vpixels_h, img, cudaMemcpyHostToDevice, s));
+    // ---- H2D on the upload stream (overlaps the previous step's compute and download) ----------------------
+    cudaStream_t up = h->h2d_stream;
+    CK(cudaMemcpyAsync(sl.means.p, means_h, 3 * N * f, cudaMemcpyHostToDevice, up));
+    CK(cudaMemcpyAsync(sl.scales.p, scales_h, 3 * N * f, cudaMemcpyHostToDevice, up));
+    CK(cudaMemcpyAsync(sl.rots.p, rotations_h, 4 * N * f, cudaMemcpyHostToDevice, up));
+    CK(cudaMemcpyAsync(sl.opac.p, opacities_h, N * f, cudaMemcpyHostToDevice, up));
+    CK(cudaMemcpyAsync(sl.shs.p, shs_h, 3 * (size_t)K * N * f, cudaMemcpyHostToDevice, up));
+    CK(cudaMemcpyAsync(sl.vpix.p, vpixels_h, img, cudaMemcpyHostToDevice, up));
+    CK(cudaEventRecord(sl.h2d_done, up));
+    CK(cudaStreamWaitEvent(s, sl.h2d_done, 0));
+    // ---- compute on the caller's stream ---------------------------------------------------------------------
     auto F = [](DevBuf &b) { return static_cast<float *>(b.p); };
-    rc = gsr_forward(h, cam, n, sh_degree, K, F(h->st_means), F(h->st_shs), F(h->st_opac), F(h->st_scales),
-                     F(h->st_rots), background, F(h->st_image), nullptr, nullptr, n_rendered, stream);
+    rc = gsr_forward(h, cam, n, sh_degree, K, F(sl.means), F(sl.shs), F(sl.opac), F(sl.scales), F(sl.rots), background,
+                     F(sl.image), nullptr, nullptr, n_rendered, stream);
     if (rc) return rc;
-    if (image_h) CK(cudaMemcpyAsync(image_h, h->st_image.p, img, cudaMemcpyDeviceToHost, s));
-    rc = gsr_backward(h, cam, n, sh_degree, K, F(h->st_means), F(h->st_shs), F(h->st_opac), F(h->st_scales),
-                      F(h->st_rots), background, F(h->st_vpix), F(h->st_vmeans), F(h->st_vshs), F(h->st_vopac),
-                      F(h->st_vscales), F(h->st_vrot), nullptr, nullptr, 0, stream);
+    cudaStream_t down = h->d2h_stream;
+    if (image_h) {  // the image can leave while the backward runs
+        CK(cudaEventRecord(sl.compute_done, s));
+        CK(cudaStreamWaitEvent(down, sl.compute_done, 0));
+        CK(cudaMemcpyAsync(image_h, sl.image.p, img, cudaMemcpyDeviceToHost, down));
+    }
+    rc = gsr_backward(h, cam, n, sh_degree, K, F(sl.means), F(sl.shs), F(sl.opac), F(sl.scales), F(sl.rots), background,
+                      F(sl.vpix), F(sl.vmeans), F(sl.vshs), F(sl.vopac), F(sl.vscales), F(sl.vrot), nullptr, nullptr, 0,
+                      stream);
     if (rc) return rc;
-    if (vmeans_h) CK(cudaMemcpyAsync(vmeans_h, h->st_vmeans.p, 3 * N * f, cudaMemcpyDeviceToHost, s));
-    if (vshs_h) CK(cudaMemcpyAsync(vshs_h, h->st_vshs.p, 3 * (size_t)K * N * f, cudaMemcpyDeviceToHost, s));
-    if (vopacities_h) CK(cudaMemcpyAsync(vopacities_h, h->st_vopac.p, N * f, cudaMemcpyDeviceToHost, s));
-    if (vscales_h) CK(cudaMemcpyAsync(vscales_h, h->st_vscales.p, 3 * N * f, cudaMemcpyDeviceToHost, s));
-    if (vrot_h) CK(cudaMemcpyAsync(vrot_h, h->st_vrot.p, 4 * N * f, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    // ---- D2H on the download stream ---------------------------------------------------------------------------
+    CK(cudaEventRecord(sl.compute_done, s));
+    CK(cudaStreamWaitEvent(down, sl.compute_done, 0));
+    if (vmeans_h) CK(cudaMemcpyAsync(vmeans_h, sl.vmeans.p, 3 * N * f, cudaMemcpyDeviceToHost, down));
+    if (vopacities_h) CK(cudaMemcpyAsync(vopacities_h, sl.vopac.p, N * f, cudaMemcpyDeviceToHost, down));
+    if (vscales_h) CK(cudaMemcpyAsync(vscales_h, sl.vscales.p, 3 * N * f, cudaMemcpyDeviceToHost, down));
+    if (vrot_h) CK(cudaMemcpyAsync(vrot_h, sl.vrot.p, 4 * N * f, cudaMemcpyDeviceToHost, down));
+    if (vshs_h) CK(cudaMemcpyAsync(vshs_h, sl.vshs.p, 3 * (size_t)K * N * f, cudaMemcpyDeviceToHost, down));
+    CK(cudaEventRecord(sl.d2h_done, down));
+    sl.d2h_pending = true;
     return GSR_OK;
+}
+
+int gsr_host_wait(GsrHandle *h) {
+    if (!h) return GSR_EINVAL;
+    for (auto &sl : h->slot)
+        if (sl.d2h_pending) { CK(cudaEventSynchronize(sl.d2h_done)); sl.d2h_pending = false; }
+    return GSR_OK;
+}
+
+int gsr_forward_backward_host(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K,
+                              const float *means_h, const float *shs_h, const float *opacities_h,
+                              const float *scales_h, const float *rotations_h, const float background[3],
+                              const float *vpixels_h, float *image_h, float *vmeans_h, float *vshs_h,
+                              float *vopacities_h, float *vscales_h, float *vrot_h, int64_t *n_rendered,
+                              void *stream) {
+    int rc = gsr_forward_backward_host_async(h, cam, n, sh_degree, K, means_h, shs_h, opacities_h, scales_h, rotations_h,
+                                             background, vpixels_h, image_h, vmeans_h, vshs_h, vopacities_h, vscales_h,
+                                             vrot_h, n_rendered, stream);
+    if (rc) return rc;
+    return gsr_host_wait(h);
 }
 
 int gsr_profile_enable(GsrHandle *h, int32_t enable) {

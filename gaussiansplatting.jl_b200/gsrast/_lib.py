@@ -38,7 +38,8 @@ class GsrStateViews(C.Structure):
 EXPORTS = ["gsr_version", "gsr_last_error", "gsr_create", "gsr_destroy", "gsr_release_scene_buffers",
            "gsr_memory_usage", "gsr_get_state", "gsr_forward", "gsr_backward", "gsr_update_stats",
            "gsr_forward_backward_host", "gsr_identify_tile_range", "gsr_sort_pairs", "gsr_launch_count",
-           "gsr_profile_enable", "gsr_profile_get", "gsr_measure_fp32_peak"]
+           "gsr_profile_enable", "gsr_profile_get", "gsr_measure_fp32_peak", "gsr_forward_backward_host_async",
+           "gsr_host_wait"]
 STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "render_fwd", "zero_grads", "render_bwd", "gauss_bwd"]
 
 
@@ -75,6 +76,8 @@ def load() -> C.CDLL:
     lib.gsr_update_stats.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.gsr_forward_backward_host.argtypes = [vp, C.POINTER(GsrCamera), i64, i32, i32, vp, vp, vp, vp, vp,
                                               C.POINTER(C.c_float), vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), vp]
+    lib.gsr_forward_backward_host_async.argtypes = lib.gsr_forward_backward_host.argtypes
+    lib.gsr_host_wait.argtypes = [vp]
     lib.gsr_identify_tile_range.argtypes = [vp, i64, vp, vp]
     lib.gsr_sort_pairs.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     lib.gsr_launch_count.restype = i64

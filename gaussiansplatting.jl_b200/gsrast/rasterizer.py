@@ -216,9 +216,11 @@ class GaussianRasterizer:
 
 
     def forward_backward_host(self, host: dict, vpixels_h, camera: Camera, sh_degree: int, background=(0.0, 0.0, 0.0),
-                              out: dict | None = None):
+                              out: dict | None = None, wait: bool = True):
         """gsr_forward_backward_host: inputs / outputs are HOST (ideally pinned) float32 torch tensors or NumPy
-        arrays; H2D of the five parameter arrays + vpixels, forward, backward, D2H of image + gradients."""
+        arrays; H2D of the five parameter arrays + vpixels, forward, backward, D2H of image + gradients.
+        wait=False submits asynchronously (gsr_forward_backward_host_async): consecutive submissions overlap their
+        transfers; call `host_wait()` before reading `out`."""
         def hp(a):
             if a is None:
                 return None
@@ -230,13 +232,17 @@ class GaussianRasterizer:
         m = C.c_int64(0)
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         with torch.cuda.device(self.device):
-            check(_lib.lib().gsr_forward_backward_host(
+            fn = _lib.lib().gsr_forward_backward_host if wait else _lib.lib().gsr_forward_backward_host_async
+            check(fn(
                 self._h, C.byref(cam), n, sh_degree, K, hp(host["means"]), hp(host["shs"]), hp(host["opac"]),
                 hp(host["scales"]), hp(host["rots"]), bg, hp(vpixels_h), hp(out.get("image")), hp(out.get("vmeans")),
                 hp(out.get("vshs")), hp(out.get("vopacities")), hp(out.get("vscales")), hp(out.get("vrot")),
                 C.byref(m), stream), self._h)
         self.n_rendered = int(m.value)
         return out
+
+    def host_wait(self):
+        check(_lib.lib().gsr_host_wait(self._h), self._h)
 
     def profile(self, enable: bool):
         check(_lib.lib().gsr_profile_enable(self._h, int(enable)), self._h)

@@ -141,15 +141,26 @@ GSR_API int gsr_backward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t 
 GSR_API int gsr_update_stats(GsrHandle *h, int64_t n, int32_t *max_radii, float *accum_grad_means2d, float *denom,
                      void *stream);
 
-/* Host-buffer convenience used for end-to-end timing: copies the five parameter arrays and vpixels from
- * (pinned) host memory, runs forward + backward, copies image and gradients back; one synchronisation at
- * the end.  Any of the host output pointers may be NULL. */
+/* Host-buffer entry points (callers whose parameters live in host memory; bench.py's end-to-end number).
+ * gsr_forward_backward_host: copies the five parameter arrays and vpixels from (pinned) host memory, runs forward +
+ * backward, copies image and gradients back, returns when the host outputs are complete.  Any host output may be NULL.
+ * gsr_forward_backward_host_async: same work, but returns once everything is enqueued (uploads on an internal
+ * H2D stream, downloads on an internal D2H stream, two staging slots), so that consecutive submissions overlap
+ * step k's compute and download with step k+1's upload; host outputs of a submission are valid after gsr_host_wait
+ * (or after two further submissions).  Inputs must stay untouched until the call returns; n_rendered is final on return. */
 GSR_API int gsr_forward_backward_host(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K,
                               const float *means_h, const float *shs_h, const float *opacities_h,
                               const float *scales_h, const float *rotations_h, const float background[3],
                               const float *vpixels_h, float *image_h, float *vmeans_h, float *vshs_h,
                               float *vopacities_h, float *vscales_h, float *vrot_h, int64_t *n_rendered,
                               void *stream);
+GSR_API int gsr_forward_backward_host_async(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K,
+                              const float *means_h, const float *shs_h, const float *opacities_h,
+                              const float *scales_h, const float *rotations_h, const float background[3],
+                              const float *vpixels_h, float *image_h, float *vmeans_h, float *vshs_h,
+                              float *vopacities_h, float *vscales_h, float *vrot_h, int64_t *n_rendered,
+                              void *stream);
+GSR_API int gsr_host_wait(GsrHandle *h);
 
 /* Stand-alone stages (known-answer tests of the reference: runtests.jl:486-494; sort yardstick). */
 /* identify_tile_range!(ranges, keys) — utils.jl:56-78; ranges_dev (2,T) must be pre-zeroed by the caller. */
