@@ -19,7 +19,7 @@ from gsrast import Camera, GaussianRasterizer
 
 AMBIG_REL = 2e-5        # math_mode="reference": sigma is bit-identical to the oracle, only exp() differs by ulps
 AMBIG_REL_FAST = 2e-4   # math_mode="fast": contracted / prescaled sigma differs by ~1e-5 absolute near the thresholds
-AMBIG_COND_FAST = 1e-6  # ... plus a few ulps of sigma's largest term (cancellation for elongated Gaussians)
+AMBIG_COND_FAST = 2.5e-6  # ... plus ~6 roundings (6e-8 each, both evaluations) of sigma's largest term (cancellation for elongated Gaussians)
 IMG_ATOL = 1e-5
 GRAD_RTOL = 1e-4
 CH = {"rgb": 3, "rgbd": 5, "rgbdn": 8}
