@@ -497,8 +497,7 @@ int gsr_forward_backward_host_async(GsrHandle *h, const GsrCamera *cam, int64_t 
     }
     GsrHandle::HostSlot &sl = h->slot[h->next_slot];
     h->next_slot ^= 1;
-    // the slot's previous download (two submissions ago) must have drained before its buffers are reused
-    if (sl.d2h_pending) { CK(cudaEventSynchronize(sl.d2h_done)); sl.d2h_pending = false; }
+    const bool reused = sl.d2h_pending;  // the slot carried the submission before the previous one
     int rc;
     if ((rc = ensure_stage(h, sl.means, 3 * N * f)) || (rc = ensure_stage(h, sl.shs, 3 * (size_t)K * N * f)) ||
         (rc = ensure_stage(h, sl.opac, N * f)) || (rc = ensure_stage(h, sl.scales, 3 * N * f)) ||
@@ -509,6 +508,12 @@ int gsr_forward_backward_host_async(GsrHandle *h, const GsrCamera *cam, int64_t 
         return rc;
     // ---- H2D on the upload stream (overlaps the previous step's compute and download) ----------------------
     cudaStream_t up = h->h2d_stream;
+    // slot reuse is ordered on the device, never on the host: the upload waits for the compute that last read this
+    // slot's inputs; the compute waits for the download that last read this slot's outputs
+    if (reused) {
+        CK(cudaStreamWaitEvent(up, sl.compute_done, 0));
+        CK(cudaStreamWaitEvent(s, sl.d2h_done, 0));
+    }
     CK(cudaMemcpyAsync(sl.means.p, means_h, 3 * N * f, cudaMemcpyHostToDevice, up));
     CK(cudaMemcpyAsync(sl.scales.p, scales_h, 3 * N * f, cudaMemcpyHostToDevice, up));
     CK(cudaMemcpyAsync(sl.rots.p, rotations_h, 4 * N * f, cudaMemcpyHostToDevice, up));

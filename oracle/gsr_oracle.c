@@ -665,12 +665,15 @@ EXPORT void orc_pack_features(int64_t n, int channels, const real *rgbs, const r
  * Gaussian) flags the Gaussian of such a pair: its gradient gains or loses that pair's whole contribution.
  * ambig_cond widens the sigma / alpha windows by ambig_cond * (|cb dx dy| + |ca dx^2|/2 + |cc dy^2|/2): a
  * contracted (FMA) evaluation of sigma differs from this one by a few ulps of its largest term, which for
- * elongated Gaussians far exceeds ulps of sigma itself (cancellation). */
+ * elongated Gaussians far exceeds ulps of sigma itself (cancellation).
+ * cond (optional, per pixel) = sum over blended pairs of alpha/(1-alpha): the first-order conditioning of the
+ * transmittance product T = prod(1-alpha) w.r.t. relative errors of alpha (a 1-ulp difference in exp() moves T, and
+ * everything composited behind, by ~1.2e-7*cond); near-opaque Gaussians (alpha -> 0.99) contribute up to 99 each. */
 EXPORT void orc_render(int channels, int32_t width, int32_t height, const uint32_t *ranges, const uint32_t *values,
                        const real *means2d, const real *opacities, const real *conics, const real *features,
                        const real *background, real *out_color, uint32_t *n_contrib, real *accum_alpha,
                        uint8_t *covis, real *uncert, int64_t *counts, int32_t tile_y0, int32_t tile_y1,
-                       uint8_t *ambig, real ambig_rel, uint8_t *ambig_g, real ambig_cond) {
+                       uint8_t *ambig, real ambig_rel, uint8_t *ambig_g, real ambig_cond, real *cond) {
     int32_t gx = (width + BLOCK - 1) / BLOCK, gy = (height + BLOCK - 1) / BLOCK;
     if (tile_y1 <= 0 || tile_y1 > gy) tile_y1 = gy;
     if (tile_y0 < 0) tile_y0 = 0;
@@ -686,7 +689,7 @@ EXPORT void orc_render(int channels, int32_t width, int32_t height, const uint32
                     real T = RC(1.0);
                     uint32_t contributor = 0, last = 0;
                     real color[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    real unc = 0;
+                    real unc = 0, kappa = 0;
                     for (uint32_t p = r0; p < r1; p++) {
                         contributor++;
                         uint32_t g = values[p] - 1;
@@ -707,6 +710,7 @@ EXPORT void orc_render(int channels, int32_t width, int32_t height, const uint32
                         const real *f = features + (int64_t)channels * g;
                         for (int c = 0; c < channels; c++) color[c] += (f[c] * alpha) * T;
                         bl_total++;
+                        kappa += alpha / (RC(1.0) - alpha);
                         if (uncert) unc += alpha * T;
                         if (covis && T > RC(0.5)) covis[g] = 1;
                         T = Tt;
@@ -717,6 +721,7 @@ EXPORT void orc_render(int channels, int32_t width, int32_t height, const uint32
                     n_contrib[pi] = last;
                     for (int c = 0; c < channels; c++) out_color[pi * channels + c] = color[c] + T * background[c];
                     if (uncert) uncert[pi] = unc;
+                    if (cond) cond[pi] = kappa;
                 }
         }
     if (counts) { counts[0] += ev_total; counts[1] += bl_total; }

@@ -81,6 +81,7 @@ class OracleState:
     counts_bwd: np.ndarray = field(default_factory=lambda: np.zeros(2, np.int64))
     ambiguous: np.ndarray = None      # (H,W)  pixels with a pair near a branch threshold
     ambiguous_g: np.ndarray = None    # (N,)   Gaussians of such pairs
+    cond: np.ndarray = None           # (H,W)  sum alpha/(1-alpha) over blended pairs (conditioning of T)
     image: np.ndarray = None
 
 
@@ -346,11 +347,12 @@ class Oracle:
         st.counts_fwd[:] = 0
         st.ambiguous = np.zeros((H, W), np.uint8) if ambig_rel is not None else None
         st.ambiguous_g = np.zeros(n, np.uint8) if ambig_rel is not None else None
+        st.cond = np.zeros((H, W), self.dtype) if ambig_rel is not None else None
         y0, y1 = tile_rows if tile_rows is not None else (0, gy)
         lib.orc_render(C.c_int(channels), C.c_int32(W), C.c_int32(H), p(st.ranges), p(st.values_sorted),
                        p(st.means2d), p(opacities), p(st.conics), p(feats), p(bg), p(image), p(st.n_contrib),
                        p(st.accum_alpha), p(covisibilities), p(uncertainties), p(st.counts_fwd),
-                       C.c_int32(y0), C.c_int32(y1), p(st.ambiguous), self.r(ambig_rel or 0.0), p(st.ambiguous_g), self.r(ambig_cond))
+                       C.c_int32(y0), C.c_int32(y1), p(st.ambiguous), self.r(ambig_rel or 0.0), p(st.ambiguous_g), self.r(ambig_cond), p(st.cond))
         return image, st
 
     # --------------------------------------------------- ∇rasterize (backward)
