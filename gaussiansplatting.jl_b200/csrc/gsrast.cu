@@ -63,10 +63,12 @@ struct GsrHandle {
     struct HostSlot {
         DevBuf means, shs, opac, scales, rots, vpix, image, vmeans, vshs, vopac, vscales, vrot;
         cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+        cudaEvent_t t_h2d0 = nullptr, t_h2d1 = nullptr, t_c0 = nullptr, t_c1 = nullptr, t_d0 = nullptr, t_d1 = nullptr;  // timeline
         bool d2h_pending = false;
     } slot[2];
     int next_slot = 0;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t t_base = nullptr;
 };
 
 namespace {
@@ -493,7 +495,10 @@ int gsr_forward_backward_host_async(GsrHandle *h, const GsrCamera *cam, int64_t 
             CK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+            for (cudaEvent_t *e : {&sl.t_h2d0, &sl.t_h2d1, &sl.t_c0, &sl.t_c1, &sl.t_d0, &sl.t_d1}) CK(cudaEventCreate(e));
         }
+        CK(cudaEventCreate(&h->t_base));
+        CK(cudaEventRecord(h->t_base, h->h2d_stream));
     }
     GsrHandle::HostSlot &sl = h->slot[h->next_slot];
     h->next_slot ^= 1;
@@ -514,14 +519,17 @@ int gsr_forward_backward_host_async(GsrHandle *h, const GsrCamera *cam, int64_t 
         CK(cudaStreamWaitEvent(up, sl.compute_done, 0));
         CK(cudaStreamWaitEvent(s, sl.d2h_done, 0));
     }
+    if (h->profile) CK(cudaEventRecord(sl.t_h2d0, up));
     CK(cudaMemcpyAsync(sl.means.p, means_h, 3 * N * f, cudaMemcpyHostToDevice, up));
     CK(cudaMemcpyAsync(sl.scales.p, scales_h, 3 * N * f, cudaMemcpyHostToDevice, up));
     CK(cudaMemcpyAsync(sl.rots.p, rotations_h, 4 * N * f, cudaMemcpyHostToDevice, up));
     CK(cudaMemcpyAsync(sl.opac.p, opacities_h, N * f, cudaMemcpyHostToDevice, up));
     CK(cudaMemcpyAsync(sl.shs.p, shs_h, 3 * (size_t)K * N * f, cudaMemcpyHostToDevice, up));
     CK(cudaMemcpyAsync(sl.vpix.p, vpixels_h, img, cudaMemcpyHostToDevice, up));
+    if (h->profile) CK(cudaEventRecord(sl.t_h2d1, up));
     CK(cudaEventRecord(sl.h2d_done, up));
     CK(cudaStreamWaitEvent(s, sl.h2d_done, 0));
+    if (h->profile) CK(cudaEventRecord(sl.t_c0, s));
     // ---- compute on the caller's stream ---------------------------------------------------------------------
     auto F = [](DevBuf &b) { return static_cast<float *>(b.p); };
     rc = gsr_forward(h, cam, n, sh_degree, K, F(sl.means), F(sl.shs), F(sl.opac), F(sl.scales), F(sl.rots), background,
@@ -538,15 +546,33 @@ int gsr_forward_backward_host_async(GsrHandle *h, const GsrCamera *cam, int64_t 
                       stream);
     if (rc) return rc;
     // ---- D2H on the download stream ---------------------------------------------------------------------------
+    if (h->profile) CK(cudaEventRecord(sl.t_c1, s));
     CK(cudaEventRecord(sl.compute_done, s));
     CK(cudaStreamWaitEvent(down, sl.compute_done, 0));
+    if (h->profile) CK(cudaEventRecord(sl.t_d0, down));
     if (vmeans_h) CK(cudaMemcpyAsync(vmeans_h, sl.vmeans.p, 3 * N * f, cudaMemcpyDeviceToHost, down));
     if (vopacities_h) CK(cudaMemcpyAsync(vopacities_h, sl.vopac.p, N * f, cudaMemcpyDeviceToHost, down));
     if (vscales_h) CK(cudaMemcpyAsync(vscales_h, sl.vscales.p, 3 * N * f, cudaMemcpyDeviceToHost, down));
     if (vrot_h) CK(cudaMemcpyAsync(vrot_h, sl.vrot.p, 4 * N * f, cudaMemcpyDeviceToHost, down));
     if (vshs_h) CK(cudaMemcpyAsync(vshs_h, sl.vshs.p, 3 * (size_t)K * N * f, cudaMemcpyDeviceToHost, down));
+    if (h->profile) CK(cudaEventRecord(sl.t_d1, down));
     CK(cudaEventRecord(sl.d2h_done, down));
     sl.d2h_pending = true;
+    return GSR_OK;
+}
+
+// debug: {h2d start, h2d end, compute start, compute end, d2h start, d2h end} of both slots, ms since the first
+// submission (valid after gsr_host_wait with profiling enabled)
+int gsr_host_timeline(GsrHandle *h, float out[12]) {
+    if (!h || !out || !h->t_base) return GSR_EINVAL;
+    for (int k = 0; k < 2; k++) {
+        cudaEvent_t ev[6] = {h->slot[k].t_h2d0, h->slot[k].t_h2d1, h->slot[k].t_c0, h->slot[k].t_c1, h->slot[k].t_d0, h->slot[k].t_d1};
+        for (int j = 0; j < 6; j++) {
+            out[6 * k + j] = 0.f;
+            if (ev[j] && cudaEventQuery(ev[j]) == cudaSuccess) cudaEventElapsedTime(&out[6 * k + j], h->t_base, ev[j]);
+        }
+    }
+    cudaGetLastError();
     return GSR_OK;
 }
 

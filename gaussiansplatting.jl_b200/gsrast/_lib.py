@@ -39,7 +39,7 @@ EXPORTS = ["gsr_version", "gsr_last_error", "gsr_create", "gsr_destroy", "gsr_re
            "gsr_memory_usage", "gsr_get_state", "gsr_forward", "gsr_backward", "gsr_update_stats",
            "gsr_forward_backward_host", "gsr_identify_tile_range", "gsr_sort_pairs", "gsr_launch_count",
            "gsr_profile_enable", "gsr_profile_get", "gsr_measure_fp32_peak", "gsr_forward_backward_host_async",
-           "gsr_host_wait"]
+           "gsr_host_wait", "gsr_host_timeline"]
 STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "render_fwd", "zero_grads", "render_bwd", "gauss_bwd"]
 
 
@@ -78,6 +78,7 @@ def load() -> C.CDLL:
                                               C.POINTER(C.c_float), vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), vp]
     lib.gsr_forward_backward_host_async.argtypes = lib.gsr_forward_backward_host.argtypes
     lib.gsr_host_wait.argtypes = [vp]
+    lib.gsr_host_timeline.argtypes = [vp, C.POINTER(C.c_float)]
     lib.gsr_identify_tile_range.argtypes = [vp, i64, vp, vp]
     lib.gsr_sort_pairs.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     lib.gsr_launch_count.restype = i64

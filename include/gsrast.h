@@ -161,6 +161,9 @@ GSR_API int gsr_forward_backward_host_async(GsrHandle *h, const GsrCamera *cam, 
                               float *vopacities_h, float *vscales_h, float *vrot_h, int64_t *n_rendered,
                               void *stream);
 GSR_API int gsr_host_wait(GsrHandle *h);
+/* debug timeline of the last two async submissions (needs gsr_profile_enable): per slot {h2d start, h2d end,
+ * compute start, compute end, d2h start, d2h end} in ms since the first submission */
+GSR_API int gsr_host_timeline(GsrHandle *h, float out[12]);
 
 /* Stand-alone stages (known-answer tests of the reference: runtests.jl:486-494; sort yardstick). */
 /* identify_tile_range!(ranges, keys) — utils.jl:56-78; ranges_dev (2,T) must be pre-zeroed by the caller. */
