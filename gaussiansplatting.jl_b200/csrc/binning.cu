@@ -120,7 +120,10 @@ scan_kernel(const int64_t n, const int32_t *__restrict__ in, int32_t *__restrict
         for (int k = 0; k < SCAN_IPT; k++)
             if (base + k < n) out[base + k] = o[k];
     }
-    if (tile == (n - 1) / SCAN_TILE && tid == SCAN_THREADS - 1) *total = s_prefix + agg;
+    if (tile == (n - 1) / SCAN_TILE && tid == SCAN_THREADS - 1) {
+        *total = s_prefix + agg;  // `total` is host-mapped pinned memory (zero-copy)
+        __threadfence_system();
+    }
 }
 
 // ----------------------------------------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 // (:416-550): the handle plays the role of `rast.{g,b,i}state` (states.jl), grown monotonically like
 // rasterizer.jl:275-278,340-343 and released by gsr_release_scene_buffers (rasterizer.jl:111-123).
 #include <atomic>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -47,8 +48,9 @@ struct GsrHandle {
     // scan
     uint32_t *scan_state = nullptr;
     size_t scan_cap = 0;  // 64-bit words
-    int64_t *total_dev = nullptr;
-    int64_t *total_host = nullptr;  // pinned
+    int64_t *total_dev = nullptr;   // device alias of total_host (zero-copy)
+    int64_t *total_host = nullptr;  // pinned + mapped: the scan kernel stores n_rendered straight into host memory, so
+                                    // the read-back never queues behind bulk D2H traffic on the copy engine
 
     // state of the last forward
     int64_t last_n = 0, last_m = 0;
@@ -267,8 +269,8 @@ int gsr_create(const GsrConfig *cfg, GsrHandle **out) {
         if ((e = dev_alloc(h, &h->ranges, 2 * (size_t)h->n_tiles)) != cudaSuccess) break;
         if ((e = dev_alloc(h, &h->n_contrib, px)) != cudaSuccess) break;
         if ((e = dev_alloc(h, &h->accum_alpha, px)) != cudaSuccess) break;
-        if ((e = dev_alloc(h, &h->total_dev, 1)) != cudaSuccess) break;
-        if ((e = cudaMallocHost(reinterpret_cast<void **>(&h->total_host), sizeof(int64_t))) != cudaSuccess) break;
+        if ((e = cudaHostAlloc(reinterpret_cast<void **>(&h->total_host), sizeof(int64_t), cudaHostAllocMapped)) != cudaSuccess) break;
+        if ((e = cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->total_dev), h->total_host, 0)) != cudaSuccess) break;
         if ((e = cudaMemset(h->ranges, 0, 2 * (size_t)h->n_tiles * 4)) != cudaSuccess) break;
         if ((e = cudaMemset(h->n_contrib, 0, px * 4)) != cudaSuccess) break;
         if ((e = cudaMemset(h->accum_alpha, 0, px * 4)) != cudaSuccess) break;
@@ -306,7 +308,6 @@ int gsr_destroy(GsrHandle *h) {
     dev_free(h, h->ranges, 2 * (size_t)h->n_tiles);
     dev_free(h, h->n_contrib, px);
     dev_free(h, h->accum_alpha, px);
-    dev_free(h, h->total_dev, 1);
     if (h->total_host) cudaFreeHost(h->total_host);
     for (cudaEvent_t e : h->ev)
         if (e) cudaEventDestroy(e);
@@ -384,11 +385,11 @@ int gsr_forward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree
         {
             StageTimer tm(h, s, GSR_STAGE_SCAN);
             launch_scan_tiles(n, h->g.tiles_touched, h->g.points_offset, h->scan_state, h->total_dev, s);
-            CK(cudaMemcpyAsync(h->total_host, h->total_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         }
         CK(cudaStreamSynchronize(s));  // the one host sync of the forward (rasterizer.jl:337)
         m = *h->total_host;
     }
+
     h->last_n = n;
     h->last_m = m;
     if (m == 0) {  // rasterizer.jl:283,338: zero image, NOT background
@@ -515,6 +516,8 @@ int gsr_forward_backward_host_async(GsrHandle *h, const GsrCamera *cam, int64_t 
     cudaStream_t up = h->h2d_stream;
     // slot reuse is ordered on the device, never on the host: the upload waits for the compute that last read this
     // slot's inputs; the compute waits for the download that last read this slot's outputs
+    // (the compute that last read this slot's inputs, two submissions ago, is already complete: the previous
+    //  submission's forward synchronised the caller's stream)
     if (reused) {
         CK(cudaStreamWaitEvent(up, sl.compute_done, 0));
         CK(cudaStreamWaitEvent(s, sl.d2h_done, 0));

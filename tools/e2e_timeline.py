@@ -12,6 +12,8 @@ vp = pin(make_vpixels(sc.width, sc.height, 5, 1002))
 out = dict(image=torch.empty((sc.height, sc.width, 5)).pin_memory(), vmeans=torch.empty((n, 3)).pin_memory(), vshs=torch.empty((n, K, 3)).pin_memory(),
            vopacities=torch.empty((n, 1)).pin_memory(), vscales=torch.empty((n, 3)).pin_memory(), vrot=torch.empty((n, 4)).pin_memory())
 rast = GaussianRasterizer(width=sc.width, height=sc.height, mode="rgbd")
+if os.environ.get("E2E_SIDE_STREAM"):
+    torch.cuda.set_stream(torch.cuda.Stream())
 for _ in range(3): rast.forward_backward_host(host, vp, cam, 3, out=out, wait=False)
 rast.host_wait(); rast.profile(True)
 t0 = time.perf_counter(); cpu = []
