@@ -126,7 +126,7 @@ def cpu_oracle_step(sc, mode, band=None):
     return t2 - t0, (t1 - t0, t2 - t1), st
 
 
-def run_reference(args):
+def run_reference(args, real_stdout):
     """--impl reference: the reference's kernels cannot run on a CPU (`@kernel cpu=false`) and there is no Julia
     toolchain, so this arm times the CPU restatement (oracle/gsr_oracle.c, kind "port") on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -167,8 +167,21 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference kernels (the Julia reference cannot execute on CPU); not the reference binary",
     }
-    print(json.dumps(line))
+    emit(line, real_stdout)
     return 0
+
+
+def emit(line: dict, real_stdout_fd: int):
+    """The ONE JSON line goes to the real stdout; everything else any library prints during the run (NCCL's version
+    banner, warnings) was diverted to stderr by `quiet_stdout`."""
+    os.write(real_stdout_fd, (json.dumps(line) + "\n").encode())
+
+
+def quiet_stdout() -> int:
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the process (C libraries included)
+    return real
 
 
 def main():
@@ -183,8 +196,9 @@ def main():
     ap.add_argument("--config", default="C2")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    real_stdout = quiet_stdout()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, real_stdout)
 
     import torch
     import torch.distributed as dist
@@ -385,7 +399,7 @@ def main():
                      "frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak, 4)},
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line))
+    emit(line, real_stdout)
     if world > 1:
         dist.destroy_process_group()
     return 0
