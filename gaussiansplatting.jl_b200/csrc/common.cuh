@@ -94,6 +94,28 @@ void launch_update_stats(int64_t n, const int32_t *radii, const float2 *grad_mea
 
 int launch_fp32_peak(cudaStream_t s, double *ms, double *flops);
 
+// ---- peer-fused per-Gaussian backward (backward_peers.cu) --------------------------------------------------
+#define GSR_MAX_PEERS 8
+struct PeerCamera {
+    float R[9], t[3], focal[2], principal[2], cam_center[3];
+    int32_t width, height;
+    float blur_eps;
+};
+struct PeerArgs {
+    PeerCamera cams[GSR_MAX_PEERS];
+    const float *gacc[GSR_MAX_PEERS];  // peer accumulators [n][AF]
+    float *table[GSR_MAX_PEERS];       // peer gradient tables: [vrot 4n | vmeans 3n | vscales 3n | vopac n | vshs 3Kn]
+    int32_t world, rank;
+    int64_t n, lo, hi;
+    int32_t sh_degree, K, channels, sh_stride;
+    int32_t vsh_aligned;  // every table's SH segment (offset 11n floats) is 16-byte aligned
+    const float *means, *shs, *opac, *scales, *rots;
+};
+void launch_pack_flags(int64_t n, int channels, const int32_t *radii, const uint8_t *clamped, float *gacc, cudaStream_t s);
+void launch_grad_means2d(int64_t n, int channels, const int32_t *radii, const float *conics, const float *gacc,
+                         float2 *out, cudaStream_t s);
+int launch_backward_gaussians_peers(const PeerArgs &args, cudaStream_t s);
+
 void count_launch(int n = 1);
 
 // get_rect — utils.jl:18-29, fp32 op order preserved (callers compile with -fmad=false or use no FMA-able form).

@@ -36,6 +36,8 @@ struct GsrHandle {
     // GeometryState
     int64_t cap_n = 0;
     GeomPtrs g{};
+    float *gacc_external = nullptr;  // caller-provided accumulator storage (symmetric / peer-mapped memory)
+    int64_t gacc_external_cap = 0;
     // BinningState
     int64_t cap_m = 0;
     uint64_t *keys_unsorted = nullptr, *keys_sorted = nullptr, *keys_tmp = nullptr;
@@ -121,7 +123,8 @@ void free_geometry(GsrHandle *h) {
     dev_free(h, h->g.radii, n);
     if (ch > 5) dev_free(h, h->g.normals, 3 * n);
     dev_free(h, h->g.rec, (size_t)rec_quads(ch) * n);
-    dev_free(h, h->g.gacc, (size_t)acc_floats(ch) * n);
+    if (h->gacc_external) h->g.gacc = nullptr;
+    else dev_free(h, h->g.gacc, (size_t)acc_floats(ch) * n);
     dev_free(h, h->scan_state, 2 * h->scan_cap);
     h->scan_cap = 0;
     h->cap_n = 0;
@@ -143,7 +146,12 @@ int ensure_geometry(GsrHandle *h, int64_t n) {
     CK(dev_alloc(h, &h->g.radii, c));
     if (ch > 5) CK(dev_alloc(h, &h->g.normals, 3 * c));
     CK(dev_alloc(h, &h->g.rec, (size_t)rec_quads(ch) * c));
-    CK(dev_alloc(h, &h->g.gacc, (size_t)acc_floats(ch) * c));
+    if (h->gacc_external) {
+        if (h->gacc_external_cap < n) return fail(h, GSR_EINVAL, "external accumulator smaller than the scene");
+        h->g.gacc = h->gacc_external;
+    } else {
+        CK(dev_alloc(h, &h->g.gacc, (size_t)acc_floats(ch) * c));
+    }
     h->scan_cap = scan_state_words(n);
     CK(dev_alloc(h, &h->scan_state, 2 * h->scan_cap));
     h->cap_n = n;
@@ -463,6 +471,89 @@ int gsr_backward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degre
                                   vshs, vopacities, vscales, vrot, vR, vt, accumulate, s);
     }
     CK(cudaGetLastError());
+    return GSR_OK;
+}
+
+int gsr_set_accumulator(GsrHandle *h, float *gacc_dev, int64_t capacity_gaussians) {
+    if (!h) return GSR_EINVAL;
+    if ((gacc_dev == nullptr) != (capacity_gaussians == 0) || (reinterpret_cast<uintptr_t>(gacc_dev) & 15))
+        return fail(h, GSR_EINVAL, "gsr_set_accumulator: need a 16-byte aligned buffer and its capacity (or NULL, 0)");
+    free_geometry(h);  // the geometry state is rebuilt around the new accumulator on the next forward
+    h->fwd_valid = false;
+    h->gacc_external = gacc_dev;
+    h->gacc_external_cap = capacity_gaussians;
+    return GSR_OK;
+}
+
+int gsr_backward_render(GsrHandle *h, int64_t n, const float background[3], const float *vpixels, void *stream) {
+    if (!h) return GSR_EINVAL;
+    if (!background || !vpixels) return fail(h, GSR_EINVAL, "gsr_backward_render: null argument");
+    if (!h->fwd_valid || n != h->last_n) return fail(h, GSR_ESTATE, "gsr_backward_render: no matching gsr_forward on this handle");
+    if (n == 0) return GSR_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int ch = h->cfg.channels;
+    {
+        StageTimer tm(h, s, GSR_STAGE_ZERO_GRADS);
+        CK(cudaMemsetAsync(h->g.gacc, 0, (size_t)n * acc_floats(ch) * sizeof(float), s));
+        launch_pack_flags(n, ch, h->g.radii, h->g.clamped, h->g.gacc, s);
+    }
+    if (h->last_m > 0) {
+        StageTimer tm(h, s, GSR_STAGE_RENDER_BWD);
+        float bg[8] = {background[0], background[1], background[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+        launch_render_backward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,
+                               bg, vpixels, h->n_contrib, h->accum_alpha, h->g.gacc, s);
+    }
+    launch_grad_means2d(n, ch, h->g.radii, h->g.conics, h->g.gacc, h->g.grad_means2d, s);
+    CK(cudaGetLastError());
+    return GSR_OK;
+}
+
+int gsr_backward_gaussians_peers(GsrHandle *h, int32_t world, int32_t rank, const GsrCamera *cams,
+                                 const float *const *peer_gacc, float *const *peer_tables, int64_t n, int32_t sh_degree,
+                                 int32_t K, const float *means, const float *shs, const float *opacities,
+                                 const float *scales, const float *rotations, void *stream) {
+    if (!h) return GSR_EINVAL;
+    if (world < 1 || world > GSR_MAX_PEERS || rank < 0 || rank >= world || !cams || !peer_gacc || !peer_tables)
+        return fail(h, GSR_EINVAL, "gsr_backward_gaussians_peers: need 1 <= world <= 8 and per-rank camera / pointer arrays");
+    if (!means || !shs || !opacities || !scales || !rotations || n < 0)
+        return fail(h, GSR_EINVAL, "gsr_backward_gaussians_peers: null parameter array");
+    if (sh_degree < 0 || sh_degree > 3 || K < (sh_degree + 1) * (sh_degree + 1))
+        return fail(h, GSR_EINVAL, "gsr_backward_gaussians_peers: need 0 <= sh_degree <= 3 and K >= (sh_degree+1)^2");
+    if (n == 0) return GSR_OK;
+    PeerArgs a;
+    memset(&a, 0, sizeof a);
+    a.vsh_aligned = 1;
+    for (int v = 0; v < world; v++) {
+        if (!peer_gacc[v] || !peer_tables[v]) return fail(h, GSR_EINVAL, "gsr_backward_gaussians_peers: null peer pointer");
+        if ((reinterpret_cast<uintptr_t>(peer_gacc[v]) & 15) || (reinterpret_cast<uintptr_t>(peer_tables[v]) & 15))
+            return fail(h, GSR_EINVAL, "gsr_backward_gaussians_peers: peer buffers must be 16-byte aligned");
+        memcpy(a.cams[v].R, cams[v].R, sizeof a.cams[v].R);
+        memcpy(a.cams[v].t, cams[v].t, sizeof a.cams[v].t);
+        memcpy(a.cams[v].focal, cams[v].focal, sizeof a.cams[v].focal);
+        memcpy(a.cams[v].principal, cams[v].principal, sizeof a.cams[v].principal);
+        memcpy(a.cams[v].cam_center, cams[v].cam_center, sizeof a.cams[v].cam_center);
+        a.cams[v].width = h->cfg.width;
+        a.cams[v].height = h->cfg.height;
+        a.cams[v].blur_eps = h->cfg.blur_eps;
+        a.gacc[v] = peer_gacc[v];
+        a.table[v] = peer_tables[v];
+        if (reinterpret_cast<uintptr_t>(peer_tables[v] + 11 * n) & 15) a.vsh_aligned = 0;
+    }
+    a.world = world;
+    a.rank = rank;
+    a.n = n;
+    int64_t chunk = (n + world - 1) / world;
+    chunk = (chunk + 63) / 64 * 64;  // slices start on a CTA boundary (16-byte aligned SH spans)
+    a.lo = rank * chunk < n ? rank * chunk : n;
+    a.hi = a.lo + chunk < n ? a.lo + chunk : n;
+    a.sh_degree = sh_degree;
+    a.K = K;
+    a.channels = h->cfg.channels;
+    a.sh_stride = (3 * K) | 1;
+    a.means = means; a.shs = shs; a.opac = opacities; a.scales = scales; a.rots = rotations;
+    StageTimer tm(h, static_cast<cudaStream_t>(stream), GSR_STAGE_GAUSS_BWD);
+    if (launch_backward_gaussians_peers(a, static_cast<cudaStream_t>(stream)) != 0)
+        return fail(h, GSR_ECUDA, "gsr_backward_gaussians_peers: launch failed");
     return GSR_OK;
 }
 

@@ -39,7 +39,8 @@ EXPORTS = ["gsr_version", "gsr_last_error", "gsr_create", "gsr_destroy", "gsr_re
            "gsr_memory_usage", "gsr_get_state", "gsr_forward", "gsr_backward", "gsr_update_stats",
            "gsr_forward_backward_host", "gsr_identify_tile_range", "gsr_sort_pairs", "gsr_launch_count",
            "gsr_profile_enable", "gsr_profile_get", "gsr_measure_fp32_peak", "gsr_forward_backward_host_async",
-           "gsr_host_wait", "gsr_host_timeline"]
+           "gsr_host_wait", "gsr_host_timeline", "gsr_set_accumulator", "gsr_backward_render",
+           "gsr_backward_gaussians_peers"]
 STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "render_fwd", "zero_grads", "render_bwd", "gauss_bwd"]
 
 
@@ -79,6 +80,10 @@ def load() -> C.CDLL:
     lib.gsr_forward_backward_host_async.argtypes = lib.gsr_forward_backward_host.argtypes
     lib.gsr_host_wait.argtypes = [vp]
     lib.gsr_host_timeline.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.gsr_set_accumulator.argtypes = [vp, vp, i64]
+    lib.gsr_backward_render.argtypes = [vp, i64, C.POINTER(C.c_float), vp, vp]
+    lib.gsr_backward_gaussians_peers.argtypes = [vp, i32, i32, C.POINTER(GsrCamera), C.POINTER(vp), C.POINTER(vp), i64, i32,
+                                                 i32, vp, vp, vp, vp, vp, vp]
     lib.gsr_identify_tile_range.argtypes = [vp, i64, vp, vp]
     lib.gsr_sort_pairs.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     lib.gsr_launch_count.restype = i64

@@ -80,3 +80,48 @@ def render_view_batch(rast, params: dict, cameras: list, vpixels: list, table: G
                        None, None, cameras[v], sh_degree, background, outs=table.outs(), accumulate=(j > 0))
     allreduce_gradients_(table, group=group)
     return mine
+
+
+class PeerFusedBackward:
+    """Per-Gaussian backward fused with the cross-GPU gradient reduction over NVLink peer memory
+    (csrc/backward_peers.cu): replaces `backward_gaussians + all_reduce(table)`.
+
+    Every rank keeps its moment accumulator (48/64 B per Gaussian) and its gradient table in symmetric memory
+    (torch.distributed._symmetric_memory).  After the local compositing backward, rank r loads all ranks' accumulator
+    rows for ITS slice of Gaussians over NVLink, applies each view's ∇project / ∇SH chain, sums, and stores the
+    reduced rows into every rank's table.  Result == the all-reduced table (same layout as `GradientTable`)."""
+
+    def __init__(self, rast, n: int, K: int, cameras: list, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        assert len(cameras) == self.world, "one camera (view) per rank"
+        self.rast, self.n, self.K, self.cameras = rast, n, K, cameras
+        af = 12 if rast.channels <= 6 else 16
+        dev = rast.device
+        self.gacc = symm_mem.empty(n * af, dtype=torch.float32, device=dev)
+        self.h_gacc = symm_mem.rendezvous(self.gacc, self.group)
+        per = 4 + 3 + 3 + 1 + 3 * K
+        self.table_flat = symm_mem.empty(n * per, dtype=torch.float32, device=dev)
+        self.h_table = symm_mem.rendezvous(self.table_flat, self.group)
+        self.gacc_ptrs = list(self.h_gacc.buffer_ptrs)
+        self.table_ptrs = list(self.h_table.buffer_ptrs)
+        rast.set_accumulator(self.gacc)
+        self.views, off = {}, 0
+        for name, s in SEGMENTS:
+            width = 3 * K if s is None else s
+            v = self.table_flat[off:off + n * width]
+            self.views[name] = v.view(n, K, 3) if s is None else v.view(n, width)
+            off += n * width
+
+    def step(self, params: dict, vpixels, sh_degree: int, background=(0.0, 0.0, 0.0)):
+        """forward + compositing backward of this rank's view, then the fused reduce; returns the table views."""
+        r, cam = self.rast, self.cameras[self.rank]
+        img = r._forward(params["means"], params["shs"], params["opac"], params["scales"], params["rots"], None, None, cam,
+                         sh_degree, background, None, None)
+        r.backward_render(vpixels, self.n, background)
+        self.h_gacc.barrier(channel=0)    # every rank's accumulator is complete
+        r.backward_gaussians_peers(self.world, self.rank, self.cameras, self.gacc_ptrs, self.table_ptrs, params["means"],
+                                   params["shs"], params["opac"], params["scales"], params["rots"], sh_degree)
+        self.h_table.barrier(channel=0)   # every rank's table is complete (and nobody still reads my accumulator)
+        return img, self.views

@@ -241,6 +241,33 @@ class GaussianRasterizer:
         self.n_rendered = int(m.value)
         return out
 
+    # ---- multi-GPU peer-fused backward (gsrast.distributed.PeerFusedBackward drives these) ------------------
+    def set_accumulator(self, gacc: torch.Tensor | None):
+        """Keep the per-Gaussian accumulator in caller-provided (symmetric / peer-mapped) memory."""
+        if gacc is None:
+            check(_lib.lib().gsr_set_accumulator(self._h, None, 0), self._h)
+        else:
+            af = 12 if self.channels <= 6 else 16
+            check(_lib.lib().gsr_set_accumulator(self._h, _ptr(gacc), gacc.numel() // af), self._h)
+        self._ext_gacc = gacc
+
+    def backward_render(self, vpixels, n, background=(0.0, 0.0, 0.0)):
+        bg = (C.c_float * 3)(*[float(b) for b in background])
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().gsr_backward_render(self._h, n, bg, _ptr(vpixels), stream), self._h)
+
+    def backward_gaussians_peers(self, world, rank, cameras, gacc_ptrs, table_ptrs, means, shs, opac, scales, rots,
+                                 sh_degree):
+        n, K = means.shape[0], shs.shape[1]
+        cams = (GsrCamera * world)(*[c.to_c() for c in cameras])
+        ga = (C.c_void_p * world)(*[int(p) for p in gacc_ptrs])
+        tb = (C.c_void_p * world)(*[int(p) for p in table_ptrs])
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().gsr_backward_gaussians_peers(self._h, world, rank, cams, ga, tb, n, sh_degree, K, _ptr(means),
+                                                          _ptr(shs), _ptr(opac), _ptr(scales), _ptr(rots), stream), self._h)
+
     def host_wait(self):
         check(_lib.lib().gsr_host_wait(self._h), self._h)
 

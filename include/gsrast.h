@@ -137,6 +137,23 @@ GSR_API int gsr_backward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t 
                  const float background[3], const float *vpixels, float *vmeans, float *vshs, float *vopacities,
                  float *vscales, float *vrot, float *vR, float *vt, int32_t accumulate, void *stream);
 
+/* ---- multi-GPU: per-Gaussian backward fused with the cross-GPU gradient reduction over peer memory -----------
+ * (not in the reference, which is single-GPU; semantics = sum over the ranks' views of ∇rasterize)
+ * gsr_set_accumulator: make the handle keep its per-Gaussian accumulator ([capacity][12 or 16] floats) in
+ *   caller-provided memory, e.g. a symmetric / peer-mapped allocation (NULL, 0 restores the private buffer).
+ * gsr_backward_render: first half of ∇rasterize — zero-fill + ∇render! into the accumulator (+ ∇means_2d).
+ * gsr_backward_gaussians_peers: second half for `world` ranks at once.  Rank `rank` owns the Gaussian slice
+ *   [rank*chunk, (rank+1)*chunk): it loads every rank's accumulator rows for that slice (peer_gacc[v], P2P loads),
+ *   applies view v's ∇project / ∇spherical_harmonics (cams[v]), sums over v and stores the reduced rows into every
+ *   rank's table (peer_tables[p], P2P stores; layout [vrot 4n | vmeans 3n | vscales 3n | vopacities n | vshs 3Kn]).
+ *   The caller separates the two halves, and the kernel from the table's consumers, with cross-rank barriers. */
+GSR_API int gsr_set_accumulator(GsrHandle *h, float *gacc_dev, int64_t capacity_gaussians);
+GSR_API int gsr_backward_render(GsrHandle *h, int64_t n, const float background[3], const float *vpixels, void *stream);
+GSR_API int gsr_backward_gaussians_peers(GsrHandle *h, int32_t world, int32_t rank, const GsrCamera *cams,
+                                 const float *const *peer_gacc, float *const *peer_tables, int64_t n, int32_t sh_degree,
+                                 int32_t K, const float *means, const float *shs, const float *opacities,
+                                 const float *scales, const float *rotations, void *stream);
+
 /* update_stats!(strategy, rast.gstate.radii, rast.gstate.∇means_2d, resolution) — strategy.jl:107-136 */
 GSR_API int gsr_update_stats(GsrHandle *h, int64_t n, int32_t *max_radii, float *accum_grad_means2d, float *denom,
                      void *stream);

@@ -20,7 +20,7 @@ for _ in range(10): x.copy_(pt)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 if rank == 0:
-    print("buffer_ptrs", [hex(p) for p in hdl.buffer_ptrs], "multicast", hdl.has_multicast_support(torch.device("cuda", local).type, local) if hasattr(hdl, "has_multicast_support") else None, hex(hdl.multicast_ptr) if hdl.multicast_ptr else None)
+    print("buffer_ptrs", [hex(p) for p in hdl.buffer_ptrs], "multicast_ptr", hex(hdl.multicast_ptr) if hdl.multicast_ptr else None)
     print("peer read ok", ok, f"{n*4/ms/1e6:.1f} GB/s peer copy")
     e0.record()
     for _ in range(20): hdl.barrier(channel=0)
