@@ -234,11 +234,32 @@ def main():
     table = GradientTable(n, K, dev)
     flat, outs = table.flat, table.outs()
 
-    def step():
+    def step_nccl():  # baseline multi-GPU path: per-rank backward over all Gaussians, then one NCCL all-reduce
         rast._forward(d["means"], d["shs"], d["opac"], d["scales"], d["rots"], None, None, cam, deg, (0, 0, 0), None, None)
         rast._backward(vpix, d["means"], d["shs"], d["opac"], d["scales"], d["rots"], None, None, cam, deg, (0, 0, 0),
                        outs=dict(outs))
         allreduce_gradients_(table)
+
+    # N > 1: per-Gaussian backward fused with the gradient reduction over NVLink peer memory (backward_peers.cu)
+    fused, reduction = None, "none (single GPU)"
+    if world > 1:
+        reduction = "NCCL all-reduce of the 59-float/Gaussian table"
+        try:
+            from gsrast.distributed import PeerFusedBackward
+            cams_all = [Camera(fx=sc.fx, fy=sc.fy, width=W, height=H, R=Rv, t=tv)
+                        for Rv, tv in (view_pose(r, world, max_yaw_deg=2.0, max_shift=0.1) for r in range(world))]
+            rast_f = GaussianRasterizer(width=W, height=H, mode=mode, math_mode=args.math, device=dev)
+            fused = PeerFusedBackward(rast_f, n, K, cams_all)
+            reduction = "peer-fused: P2P loads of the moment accumulators + P2P stores of the reduced rows (NVLink)"
+        except Exception as e:  # symmetric memory unavailable: keep the NCCL path
+            sys.stderr.write(f"[bench] peer-fused path unavailable ({e}); using NCCL all-reduce\n")
+            fused = None
+
+    def step():
+        if fused is not None:
+            fused.step(d, vpix, deg)
+        else:
+            step_nccl()
 
     def barrier():
         torch.cuda.synchronize()
@@ -269,6 +290,19 @@ def main():
     clocks = sampler.stop(w0, w1) if sampler else None
     ms_per_step = total_ms / args.steps
     value = world * args.steps / (total_ms * 1e-3)
+    nccl_value = None
+    if world > 1 and fused is not None:  # the same step with backward_gaussians + NCCL all-reduce, for comparison
+        for _ in range(3):
+            step_nccl()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step_nccl()
+        e1.record()
+        barrier()
+        msn = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(msn, op=dist.ReduceOp.MAX)
+        nccl_value = world * args.steps / (float(msn.item()) * 1e-3)
 
     # ---- end to end: host buffers in, host buffers out ------------------------------------------------------
     e2e = None
@@ -286,13 +320,18 @@ def main():
             else:
                 dd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
                 vp = vpix_h.to(dev, non_blocking=True)
-                img = rast._forward(dd["means"], dd["shs"], dd["opac"], dd["scales"], dd["rots"], None, None, cam, deg,
-                                    (0, 0, 0), None, None)
-                rast._backward(vp, dd["means"], dd["shs"], dd["opac"], dd["scales"], dd["rots"], None, None, cam, deg,
-                               (0, 0, 0), outs=dict(outs))
-                allreduce_gradients_(table)
+                if fused is not None:
+                    img, _ = fused.step(dd, vp, deg)
+                    src_flat = fused.table_flat
+                else:
+                    img = rast._forward(dd["means"], dd["shs"], dd["opac"], dd["scales"], dd["rots"], None, None, cam,
+                                        deg, (0, 0, 0), None, None)
+                    rast._backward(vp, dd["means"], dd["shs"], dd["opac"], dd["scales"], dd["rots"], None, None, cam, deg,
+                                   (0, 0, 0), outs=dict(outs))
+                    allreduce_gradients_(table)
+                    src_flat = flat
                 out_h["image"].copy_(img, non_blocking=True)
-                flat_h.copy_(flat, non_blocking=True)
+                flat_h.copy_(src_flat, non_blocking=True)
                 torch.cuda.synchronize()
 
         for _ in range(3):
@@ -313,7 +352,7 @@ def main():
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(mse.item()) / ke, "steps": ke,
                "api": "gsr_forward_backward_host_async + gsr_host_wait (C ABI, pinned host buffers, double-buffered "
                       "staging: H2D / compute / D2H of consecutive steps overlap)" if world == 1 else
-                      "pinned torch copies + gsr_forward/gsr_backward + NCCL all-reduce + D2H"}
+                      "pinned torch copies + gsr_forward / backward + gradient reduction + D2H"}
 
     if rank != 0:
         if world > 1:
@@ -391,7 +430,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "N": n, "V": V, "M": M, "tiles": T, "sh_degree": deg, "mode": mode,
                    "math_mode": args.math, "views_per_step_per_gpu": 1,
-                   "parallelism": f"view-sharded x{world}" + (" + NCCL all-reduce of gradients" if world > 1 else ""),
+                   "parallelism": f"view-sharded x{world}", "gradient_reduction": reduction,
+                   "value_with_nccl_allreduce": nccl_value,
                    "l2": "inputs larger than L2: 236 MB parameters + 236 MB gradients + ~0.5 GB state per step vs 126 MB L2"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": roofline, "roofline_fp32": roofline_fp32, "stages": stages,
