@@ -91,24 +91,7 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
     const bool aligned16 = (((uintptr_t)shs | (uintptr_t)vshs) & 15) == 0;
     if (__syncthreads_or(visible_t) && sh_degree > 0) {
         if (k_used == K) {
-            const float *src = shs + block0 * row;
-            const int64_t nq = aligned16 ? (span >> 2) : 0;
-            for (int64_t q = tid; q < nq; q += BG_THREADS) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + q);
-                const int e = (int)(q << 2);
-                const int gq = e / row, rq = e - gq * row;
-                const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    int gg = gq, rr = rq + u;
-                    if (rr >= row) { rr -= row; gg += 1; }
-                    s_sh[gg * sh_stride + rr] = vv[u];
-                }
-            }
-            for (int64_t e = (nq << 2) + tid; e < span; e += BG_THREADS) {
-                const int gg = (int)(e / row), rr = (int)(e - (int64_t)gg * row);
-                s_sh[gg * sh_stride + rr] = src[e];
-            }
+            rows_global_to_shared(shs + block0 * row, s_sh, (int)nb, row, sh_stride, tid, BG_THREADS, aligned16);
         } else if (visible_t) {
             const float *src = shs + i * (int64_t)row;
             for (int e = 0; e < 3 * k_used; e++) s_sh[tid * sh_stride + e] = src[e];
@@ -422,30 +405,7 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
     // coalesced write-out of the CTA's SH-gradient span
     __syncthreads();
     {
-        float *dst = vshs + block0 * row;
-        const int64_t nq = aligned16 ? (span >> 2) : 0;
-        for (int64_t q = tid; q < nq; q += BG_THREADS) {
-            const int e = (int)(q << 2);
-            const int gq = e / row, rq = e - gq * row;
-            float vv[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                int gg = gq, rr = rq + u;
-                if (rr >= row) { rr -= row; gg += 1; }
-                vv[u] = s_sh[gg * sh_stride + rr];
-            }
-            float4 *d4 = reinterpret_cast<float4 *>(dst) + q;
-            if (ACC) {
-                const float4 o = *d4;
-                *d4 = make_float4(o.x + vv[0], o.y + vv[1], o.z + vv[2], o.w + vv[3]);
-            } else {
-                *d4 = make_float4(vv[0], vv[1], vv[2], vv[3]);
-            }
-        }
-        for (int64_t e = (nq << 2) + tid; e < span; e += BG_THREADS) {
-            const int gg = (int)(e / row), rr = (int)(e - (int64_t)gg * row);
-            put<ACC>(dst + e, s_sh[gg * sh_stride + rr]);
-        }
+        rows_shared_to_global<ACC>(vshs + block0 * row, s_sh, (int)nb, row, sh_stride, tid, BG_THREADS, aligned16);
     }
 
     if (pose) {  // CTA-level reduction of the 12 pose cotangents before one atomic each (TODO at projection.jl:242)

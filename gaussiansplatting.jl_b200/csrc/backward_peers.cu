@@ -116,10 +116,7 @@ backward_gaussians_peers_kernel(const PeerArgs A) {
     if (A.sh_degree > 0) {
         const float *src = A.shs + block0 * row;
         if (k_used == A.K) {
-            for (int64_t e = tid; e < span; e += BP_THREADS) {
-                const int gg = (int)(e / row), rr = (int)(e - (int64_t)gg * row);
-                s_sh[gg * stride + rr] = __ldg(src + e);
-            }
+            rows_global_to_shared(src, s_sh, (int)nb, row, stride, tid, BP_THREADS, (reinterpret_cast<uintptr_t>(src) & 15) == 0);
         } else if (in) {
             const float *s1 = A.shs + i * (int64_t)row;
             for (int e = 0; e < 3 * k_used; e++) s_sh[tid * stride + e] = s1[e];

@@ -118,6 +118,83 @@ int launch_backward_gaussians_peers(const PeerArgs &args, cudaStream_t s);
 
 void count_launch(int n = 1);
 
+// ---- coalesced copy between a contiguous span of `nb` rows of `row` floats in global memory and per-thread padded
+// rows in shared memory (row g at s + g*stride).  128-bit global accesses when `aligned16`; the (row, column)
+// of each quad is advanced incrementally (two integer divisions per thread in total, none in the loop).
+__device__ __forceinline__ void rows_global_to_shared(const float *__restrict__ src, float *s, const int nb,
+                                                      const int row, const int stride, const int tid,
+                                                      const int nthreads, const bool aligned16) {
+    const int total = nb * row;
+    const int nq = aligned16 ? (total >> 2) : 0;
+    if (nq > 0) {
+        const int step = 4 * nthreads, step_g = step / row, step_r = step - step_g * row;
+        int e = 4 * tid, g = e / row, r = e - g * row;
+        const bool whole = (row & 3) == 0;  // a quad never straddles two rows
+        for (int q0 = tid; q0 < nq; q0 += 4 * nthreads) {  // 4 independent 128-bit loads in flight per thread
+            float4 v4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (q0 + j * nthreads < nq) v4[j] = __ldg(reinterpret_cast<const float4 *>(src) + q0 + j * nthreads);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (q0 + j * nthreads < nq) {
+                    const float4 v = v4[j];
+                    float *d = s + g * stride + r;
+                    if (whole) {
+                        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                    } else {
+                        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int u = 0; u < 4; u++) d[r + u >= row ? u + stride - row : u] = vv[u];
+                    }
+                    r += step_r; g += step_g;
+                    if (r >= row) { r -= row; g += 1; }
+                }
+            }
+        }
+    }
+    for (int e = (nq << 2) + tid; e < total; e += nthreads) {
+        const int g = e / row, r = e - g * row;
+        s[g * stride + r] = __ldg(src + e);
+    }
+}
+template <bool ACC>
+__device__ __forceinline__ void rows_shared_to_global(float *__restrict__ dst, const float *s, const int nb,
+                                                      const int row, const int stride, const int tid,
+                                                      const int nthreads, const bool aligned16) {
+    const int total = nb * row;
+    const int nq = aligned16 ? (total >> 2) : 0;
+    if (nq > 0) {
+        const int step = 4 * nthreads, step_g = step / row, step_r = step - step_g * row;
+        int e = 4 * tid, g = e / row, r = e - g * row;
+        const bool whole = (row & 3) == 0;
+        for (int q = tid; q < nq; q += nthreads) {
+            const float *p = s + g * stride + r;
+            float4 v;
+            if (whole) {
+                v = make_float4(p[0], p[1], p[2], p[3]);
+            } else {
+                float vv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) vv[u] = p[r + u >= row ? u + stride - row : u];
+                v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            }
+            float4 *d4 = reinterpret_cast<float4 *>(dst) + q;
+            if (ACC) {
+                const float4 o = *d4;
+                v = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
+            }
+            *d4 = v;
+            r += step_r; g += step_g;
+            if (r >= row) { r -= row; g += 1; }
+        }
+    }
+    for (int e = (nq << 2) + tid; e < total; e += nthreads) {
+        const int g = e / row, r = e - g * row;
+        if (ACC) dst[e] += s[g * stride + r]; else dst[e] = s[g * stride + r];
+    }
+}
+
 // get_rect — utils.jl:18-29, fp32 op order preserved (callers compile with -fmad=false or use no FMA-able form).
 __device__ __forceinline__ void get_rect(float px, float py, int32_t radius, int32_t gx, int32_t gy, int32_t &x0,
                                          int32_t &y0, int32_t &x1, int32_t &y1) {

@@ -179,34 +179,8 @@ preprocess_kernel(const DevCamera cam, const int64_t n, const int sh_degree, con
     const bool any_visible = __syncthreads_or(visible);
     if (any_visible) {
         if (k_used == K) {
-            const int64_t nb = (n - block0) < PP_THREADS ? (n - block0) : PP_THREADS;
-            const int row = 3 * K;
-            const int64_t total = nb * row;
-            const float *src = shs + block0 * row;
-            if (ALIGNED16) {
-                const int64_t nq = total >> 2;
-                for (int64_t q = tid; q < nq; q += PP_THREADS) {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + q);
-                    const int e = (int)(q << 2);
-                    const int gq = e / row, rq = e - gq * row;  // row % 4 may be != 0: split element-wise
-                    const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        int gg = gq, rr = rq + u;
-                        if (rr >= row) { rr -= row; gg += 1; }
-                        s_sh[gg * sh_stride + rr] = vv[u];
-                    }
-                }
-                for (int64_t e = (nq << 2) + tid; e < total; e += PP_THREADS) {
-                    const int gg = (int)(e / row), rr = (int)(e - (int64_t)gg * row);
-                    s_sh[gg * sh_stride + rr] = src[e];
-                }
-            } else {
-                for (int64_t e = tid; e < total; e += PP_THREADS) {
-                    const int gg = (int)(e / row), rr = (int)(e - (int64_t)gg * row);
-                    s_sh[gg * sh_stride + rr] = src[e];
-                }
-            }
+            const int nb = (int)((n - block0) < PP_THREADS ? (n - block0) : PP_THREADS);
+            rows_global_to_shared(shs + block0 * (int64_t)(3 * K), s_sh, nb, 3 * K, sh_stride, tid, PP_THREADS, ALIGNED16);
         } else if (visible) {  // k_used < K: only the leading coefficients are needed — direct strided loads
             const float *src = shs + i * (int64_t)(3 * K);
             for (int e = 0; e < 3 * k_used; e++) s_sh[tid * sh_stride + e] = src[e];

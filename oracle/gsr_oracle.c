@@ -666,9 +666,13 @@ EXPORT void orc_pack_features(int64_t n, int channels, const real *rgbs, const r
  * ambig_cond widens the sigma / alpha windows by ambig_cond * (|cb dx dy| + |ca dx^2|/2 + |cc dy^2|/2): a
  * contracted (FMA) evaluation of sigma differs from this one by a few ulps of its largest term, which for
  * elongated Gaussians far exceeds ulps of sigma itself (cancellation).
- * cond (optional, per pixel) = sum over blended pairs of alpha/(1-alpha): the first-order conditioning of the
- * transmittance product T = prod(1-alpha) w.r.t. relative errors of alpha (a 1-ulp difference in exp() moves T, and
- * everything composited behind, by ~1.2e-7*cond); near-opaque Gaussians (alpha -> 0.99) contribute up to 99 each. */
+ * cond (optional, per pixel) = sum over blended pairs of (alpha/(1-alpha) + alpha*T) * (1 + S/2), S = the sum of the
+ * magnitudes of sigma's three terms: the first-order bound, in units of the relative error eps of one exp(), of the
+ * pixel's colour error when every alpha carries a relative error eps*(1 + S/2) — eps from exp() itself plus half
+ * an eps per unit of sigma's largest term (a differently ordered / contracted evaluation of the quadratic form;
+ * cancellation makes that dominant for elongated Gaussians).  alpha/(1-alpha) is the conditioning of the
+ * transmittance product behind the pair (near-opaque Gaussians, alpha -> 0.99, contribute up to 99 each),
+ * alpha*T the pair's own weight. */
 EXPORT void orc_render(int channels, int32_t width, int32_t height, const uint32_t *ranges, const uint32_t *values,
                        const real *means2d, const real *opacities, const real *conics, const real *features,
                        const real *background, real *out_color, uint32_t *n_contrib, real *accum_alpha,
@@ -697,8 +701,9 @@ EXPORT void orc_render(int channels, int32_t width, int32_t height, const uint32
                         const real *cn = conics + 3 * (int64_t)g;
                         real sigma = (cn[1] * dx) * dy + RC(0.5) * (cn[0] * (dx * dx) + cn[2] * (dy * dy));
                         ev_total++;
-                        real win = ambig_rel;
-                        if (ambig) win += ambig_cond * (R_FABS((cn[1] * dx) * dy) + RC(0.5) * (R_FABS(cn[0] * (dx * dx)) + R_FABS(cn[2] * (dy * dy))));
+                        real win = ambig_rel, S = 0;
+                        if (ambig || cond) S = R_FABS((cn[1] * dx) * dy) + RC(0.5) * (R_FABS(cn[0] * (dx * dx)) + R_FABS(cn[2] * (dy * dy)));
+                        if (ambig) win += ambig_cond * S;
                         if (ambig && R_FABS(sigma) <= win) { ambig[(int64_t)py * width + px] = 1; if (ambig_g) ambig_g[g] = 1; }
                         if (sigma < (real)0) continue;
                         real alpha = rmin_(RC(0.99), opacities[g] * R_EXP(-sigma));
@@ -710,7 +715,7 @@ EXPORT void orc_render(int channels, int32_t width, int32_t height, const uint32
                         const real *f = features + (int64_t)channels * g;
                         for (int c = 0; c < channels; c++) color[c] += (f[c] * alpha) * T;
                         bl_total++;
-                        kappa += alpha / (RC(1.0) - alpha);
+                        kappa += (alpha / (RC(1.0) - alpha) + alpha * T) * (RC(1.0) + RC(0.5) * S);
                         if (uncert) unc += alpha * T;
                         if (covis && T > RC(0.5)) covis[g] = 1;
                         T = Tt;

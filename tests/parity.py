@@ -103,9 +103,11 @@ def assert_image_close(img, st, ref_img, strict=False, max_ambig_frac=0.02):
     strict=True (math_mode="reference"): 1e-5 ABSOLUTE on every channel, depth included — the letter of north_star.
     strict=False (math_mode="fast"): 1e-5 * featmax_c + EPS_FAST * cond * featmax_c per pixel and channel, where
     featmax_c is the largest per-Gaussian feature of the channel (1 for rgb/alpha/normal, the far visible depth for
-    the depth channel) and cond = sum alpha/(1-alpha) over the pixel's blended pairs is the conditioning of the
-    transmittance product: ex2.approx (2 ulp) vs expf moves T — and everything composited behind a near-opaque
-    Gaussian — by up to 2.5e-7 * cond.  The reference on a GPU (libdevice expf, <= 2 ulp) has the same sensitivity."""
+    the depth channel) and cond is the oracle's first-order error amplification of the pixel (orc_render): every
+    alpha of the fast path differs from the reference-order one by up to EPS_FAST (ex2.approx, 2 ulp) plus half
+    of that per unit of sigma's largest term (FMA-contracted, prescaled quadratic form); the pair's own weight
+    alpha*T and the transmittance of everything behind it (conditioning alpha/(1-alpha)) inherit that error.  The
+    reference on a GPU (libdevice expf <= 2 ulp, LLVM-contracted sigma) has the same sensitivity."""
     img = np_(img)
     C = img.shape[2]
     ok = st.ambiguous == 0
@@ -120,7 +122,9 @@ def assert_image_close(img, st, ref_img, strict=False, max_ambig_frac=0.02):
         tol = tol + EPS_FAST * st.cond.astype(np.float64)[:, :, None] * featmax[None, None, :]
     bad = (d > tol) & ok[:, :, None]
     assert not bad.any(), (f"{bad.sum()} non-ambiguous values beyond tolerance (featmax {featmax.tolist()}): max err per channel "
-                           f"{[float(d[:, :, c][ok].max()) for c in range(C)]} at {np.argwhere(bad)[:5].tolist()}")
+                           f"{[float(d[:, :, c][ok].max()) for c in range(C)]} at {np.argwhere(bad)[:5].tolist()}; "
+                           f"(err, tol, cond, T, n_contrib) there: "
+                           f"{[(float(d[tuple(i)]), float(tol[tuple(i)]), float(st.cond[i[0], i[1]]), float(st.accum_alpha[i[0], i[1]]), int(st.n_contrib[i[0], i[1]])) for i in np.argwhere(bad)[:5]]}")
     scale = max(1.0, float(np.abs(ref_img).max()))
     assert d.max() <= 2e-2 * scale, f"ambiguous pixel error {d.max():.3e} too large for a single flipped pair"
     return dict(max_err=float(d[ok].max()) if ok.any() else 0.0,
