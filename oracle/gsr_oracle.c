@@ -898,4 +898,128 @@ EXPORT void orc_update_stats(int64_t n, const int32_t *radii, const real *vmeans
     }
 }
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused SSIM — fused_ssim.jl.  Arrays are the reference's (W,H,CH,B) column-major, i.e.
+ * planar [b][c][y][x].  11-tap separable window (fused_ssim.jl:11-24: sigma = 1.5, normalised; the literals
+ * are the reference's float32 constants — entry 4 is one ulp below the correctly rounded formula value, so
+ * they are data, not derivable), zero padding outside the image (get_pix_value, :27-31).
+ * Op order of the two passes (:83-112, :170-205): pairs (left + right) * w for d = 1..5 with w = G[5 - d],
+ * then the centre tap; squares and products are formed per tap before the pair sum.
+ * ------------------------------------------------------------------------------------------------------- */
+static const float SSIM_G[11] = {0.001028380123898387f, 0.0075987582094967365f, 0.036000773310661316f,
+                                 0.10936068743467331f,  0.21300552785396576f,  0.26601171493530273f,
+                                 0.21300552785396576f,  0.10936068743467331f,  0.036000773310661316f,
+                                 0.0075987582094967365f, 0.001028380123898387f};
+
+static inline real ssim_pix(const real *plane, int32_t W, int32_t H, int32_t y, int32_t x) {
+    return (x < 0 || x >= W || y < 0 || y >= H) ? (real)0 : plane[(int64_t)y * W + x];
+}
+
+/* _fused_ssim! — fused_ssim.jl:34-258.  ssim_map always; the three partial-derivative maps when train != 0. */
+EXPORT void orc_fused_ssim(int32_t W, int32_t H, int32_t CH, int32_t B, const real *img, const real *ref, real C1,
+                           real C2, int train, real *ssim_map, real *dm_dmu1, real *dm_dsigma1_sq, real *dm_dsigma12) {
+    const int64_t plane = (int64_t)W * H;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t pc = 0; pc < (int64_t)CH * B; pc++) {
+        const real *X = img + pc * plane, *Y = ref + pc * plane;
+        /* horizontal pass on rows -5 .. H+4 (rows outside the image are all-zero inputs -> exact zeros) */
+        real *xc = (real *)malloc(sizeof(real) * 5 * (size_t)(H + 10) * W);
+        for (int32_t yy = -5; yy < H + 5; yy++)
+            for (int32_t x = 0; x < W; x++) {
+                real sX = 0, sX2 = 0, sY = 0, sY2 = 0, sXY = 0;
+                for (int d = 1; d <= 5; d++) {
+                    real w = (real)SSIM_G[5 - d];
+                    real Xl = ssim_pix(X, W, H, yy, x - d), Yl = ssim_pix(Y, W, H, yy, x - d);
+                    real Xr = ssim_pix(X, W, H, yy, x + d), Yr = ssim_pix(Y, W, H, yy, x + d);
+                    sX += (Xl + Xr) * w;
+                    sX2 += (Xl * Xl + Xr * Xr) * w;
+                    sY += (Yl + Yr) * w;
+                    sY2 += (Yl * Yl + Yr * Yr) * w;
+                    sXY += (Xl * Yl + Xr * Yr) * w;
+                }
+                real cx = ssim_pix(X, W, H, yy, x), cy = ssim_pix(Y, W, H, yy, x), wc = (real)SSIM_G[5];
+                sX += cx * wc;
+                sX2 += cx * cx * wc;
+                sY += cy * wc;
+                sY2 += cy * cy * wc;
+                sXY += cx * cy * wc;
+                real *o = xc + 5 * ((int64_t)(yy + 5) * W + x);
+                o[0] = sX; o[1] = sX2; o[2] = sY; o[3] = sY2; o[4] = sXY;
+            }
+        for (int32_t y = 0; y < H; y++)
+            for (int32_t x = 0; x < W; x++) {
+                real out[5] = {0, 0, 0, 0, 0};
+                for (int d = 1; d <= 5; d++) {
+                    real w = (real)SSIM_G[5 - d];
+                    const real *top = xc + 5 * ((int64_t)(y + 5 - d) * W + x), *bot = xc + 5 * ((int64_t)(y + 5 + d) * W + x);
+                    for (int k = 0; k < 5; k++) out[k] += (top[k] + bot[k]) * w;
+                }
+                const real *ctr = xc + 5 * ((int64_t)(y + 5) * W + x);
+                for (int k = 0; k < 5; k++) out[k] += ctr[k] * (real)SSIM_G[5];
+                real mu1 = out[0], mu2 = out[2];
+                real mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2;
+                real sigma1_sq = out[1] - mu1_sq, sigma2_sq = out[3] - mu2_sq, sigma12 = out[4] - mu1 * mu2;
+                real A = mu1_sq + mu2_sq + C1, Bv = sigma1_sq + sigma2_sq + C2;
+                real Cv = RC(2.0) * mu1 * mu2 + C1, Dv = RC(2.0) * sigma12 + C2;
+                int64_t o = pc * plane + (int64_t)y * W + x;
+                ssim_map[o] = (Cv * Dv) / (A * Bv);
+                if (train) {
+                    dm_dmu1[o] = (mu2 * RC(2.0) * Dv) / (A * Bv) - (mu2 * RC(2.0) * Cv) / (A * Bv) -
+                                 (mu1 * RC(2.0) * Cv * Dv) / (A * A * Bv) + (mu1 * RC(2.0) * Cv * Dv) / (A * Bv * Bv);
+                    dm_dsigma1_sq[o] = (-Cv * Dv) / (A * Bv * Bv);
+                    dm_dsigma12[o] = (RC(2.0) * Cv) / (A * Bv);
+                }
+            }
+        free(xc);
+    }
+}
+
+/* _fused_ssim_bwd! — fused_ssim.jl:261-352.  dL_dimg = conv(dm_dmu1*dL) + 2*img*conv(dm_dsigma1_sq*dL) + ref*conv(dm_dsigma12*dL). */
+EXPORT void orc_fused_ssim_bwd(int32_t W, int32_t H, int32_t CH, int32_t B, const real *img, const real *ref,
+                               const real *dL_dmap, const real *dm_dmu1, const real *dm_dsigma1_sq,
+                               const real *dm_dsigma12, real *dL_dimg) {
+    const int64_t plane = (int64_t)W * H;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t pc = 0; pc < (int64_t)CH * B; pc++) {
+        const real *L = dL_dmap + pc * plane, *M0 = dm_dmu1 + pc * plane, *M1 = dm_dsigma1_sq + pc * plane,
+                   *M2 = dm_dsigma12 + pc * plane;
+        real *sc = (real *)malloc(sizeof(real) * 3 * (size_t)(H + 10) * W);
+        for (int32_t yy = -5; yy < H + 5; yy++)
+            for (int32_t x = 0; x < W; x++) {
+                real a[3] = {0, 0, 0};
+                for (int d = 1; d <= 5; d++) {
+                    real w = (real)SSIM_G[5 - d];
+                    real cl = ssim_pix(L, W, H, yy, x - d), cr = ssim_pix(L, W, H, yy, x + d);
+                    real l0 = ssim_pix(M0, W, H, yy, x - d) * cl, r0 = ssim_pix(M0, W, H, yy, x + d) * cr;
+                    real l1 = ssim_pix(M1, W, H, yy, x - d) * cl, r1 = ssim_pix(M1, W, H, yy, x + d) * cr;
+                    real l2 = ssim_pix(M2, W, H, yy, x - d) * cl, r2 = ssim_pix(M2, W, H, yy, x + d) * cr;
+                    a[0] += (l0 + r0) * w;
+                    a[1] += (l1 + r1) * w;
+                    a[2] += (l2 + r2) * w;
+                }
+                real cc = ssim_pix(L, W, H, yy, x), wc = (real)SSIM_G[5];
+                a[0] += (ssim_pix(M0, W, H, yy, x) * cc) * wc;
+                a[1] += (ssim_pix(M1, W, H, yy, x) * cc) * wc;
+                a[2] += (ssim_pix(M2, W, H, yy, x) * cc) * wc;
+                real *o = sc + 3 * ((int64_t)(yy + 5) * W + x);
+                o[0] = a[0]; o[1] = a[1]; o[2] = a[2];
+            }
+        for (int32_t y = 0; y < H; y++)
+            for (int32_t x = 0; x < W; x++) {
+                real s[3] = {0, 0, 0};
+                for (int d = 1; d <= 5; d++) {
+                    real w = (real)SSIM_G[5 - d];
+                    const real *top = sc + 3 * ((int64_t)(y + 5 - d) * W + x), *bot = sc + 3 * ((int64_t)(y + 5 + d) * W + x);
+                    for (int k = 0; k < 3; k++) s[k] += (top[k] + bot[k]) * w;
+                }
+                const real *ctr = sc + 3 * ((int64_t)(y + 5) * W + x);
+                for (int k = 0; k < 3; k++) s[k] += ctr[k] * (real)SSIM_G[5];
+                int64_t o = pc * plane + (int64_t)y * W + x;
+                dL_dimg[o] = s[0] + RC(2.0) * img[o] * s[1] + ref[o] * s[2];
+            }
+        free(sc);
+    }
+}
+
+
 EXPORT int orc_real_size(void) { return (int)sizeof(real); }

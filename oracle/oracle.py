@@ -278,6 +278,53 @@ class Oracle:
                                   self.p(self.arr(grad_means2d)), C.c_uint32(width), C.c_uint32(height),
                                   self.p(max_radii), self.p(accum), self.p(denom))
 
+    # ------------------------------------------------- fused SSIM (§8f-2)
+    def fused_ssim(self, img, ref, C1=0.01 ** 2, C2=0.03 ** 2, train=True):
+        """`_fused_ssim` — fused_ssim.jl:354-372.  img/ref: (B,CH,H,W) C-contiguous == the reference's (W,H,CH,B).
+        Returns (ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12); the last three are None when train is False."""
+        img, ref = self.arr(img), self.arr(ref)
+        B, CH, H, W = img.shape
+        assert ref.shape == img.shape
+        out = np.zeros_like(img)
+        d = [np.zeros_like(img) for _ in range(3)] if train else [None, None, None]
+        c1, c2 = float(np.float32(C1)), float(np.float32(C2))  # Float32 keyword defaults of the reference
+        self.lib.orc_fused_ssim(C.c_int32(W), C.c_int32(H), C.c_int32(CH), C.c_int32(B), self.p(img), self.p(ref),
+                                self.r(c1), self.r(c2), C.c_int(1 if train else 0), self.p(out), self.p(d[0]),
+                                self.p(d[1]), self.p(d[2]))
+        return out, d[0], d[1], d[2]
+
+    def fused_ssim_bwd(self, img, ref, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12):
+        """`fused_ssim_bwd` — fused_ssim.jl:374-389."""
+        img, ref, dL = self.arr(img), self.arr(ref), self.arr(dL_dmap)
+        B, CH, H, W = img.shape
+        out = np.zeros_like(img)
+        self.lib.orc_fused_ssim_bwd(C.c_int32(W), C.c_int32(H), C.c_int32(CH), C.c_int32(B), self.p(img), self.p(ref),
+                                    self.p(dL), self.p(self.arr(dm_dmu1)), self.p(self.arr(dm_dsigma1_sq)),
+                                    self.p(self.arr(dm_dsigma12)), self.p(out))
+        return out
+
+    def photometric_loss(self, image_hwc, target, lambda_dssim=0.2):
+        """The loss either side of the rasterizer (training.jl:684-694) and its pullback to the raster image:
+        image_hwc (H,W,C) with rgb in channels 0..2, target (3,H,W) == the reference's (W,H,3,1).
+        total = (1-l)*mean|x - t| + l*(1 - mean(fused_ssim(x; ref=t))).  Returns (total, l1, ssim_mean, vpixels (H,W,C))."""
+        image_hwc = self.arr(image_hwc)
+        H, W, Cc = image_hwc.shape
+        x = np.ascontiguousarray(image_hwc[:, :, :3].transpose(2, 0, 1))[None]       # (1,3,H,W): permutedims + reshape
+        t = self.arr(target).reshape(1, 3, H, W)
+        lam = self.dtype.type(lambda_dssim)
+        one = self.dtype.type(1)
+        npc = x.size
+        l1 = np.abs(x - t).mean(dtype=np.float64)
+        m, d0, d1, d2 = self.fused_ssim(x, t, train=True)
+        sm = m.mean(dtype=np.float64)
+        total = float((one - lam)) * l1 + float(lam) * (1.0 - sm)
+        dmap = np.full_like(x, -float(lam) / npc)
+        g = self.fused_ssim_bwd(x, t, dmap, d0, d1, d2).astype(np.float64)
+        g += float(one - lam) / npc * np.sign(x.astype(np.float64) - t.astype(np.float64))
+        v = np.zeros((H, W, Cc), self.dtype)
+        v[:, :, :3] = g[0].transpose(1, 2, 0).astype(self.dtype)
+        return total, float(l1), float(sm), v
+
     # ---------------------------------------------------- rasterize (forward)
     def forward(self, means, shs, opacities, scales, rotations, cam: OracleCamera, *, mode="rgbd", sh_degree=0,
                 background=(0.0, 0.0, 0.0), near=0.2, far=1000.0, covisibilities=None, uncertainties=None,
