@@ -118,6 +118,15 @@ int launch_backward_gaussians_peers(const PeerArgs &args, cudaStream_t s);
 
 void count_launch(int n = 1);
 
+// ---- fused SSIM / photometric loss (ssim.cu) -----------------------------------------------------------------
+int launch_ssim_forward(int W, int H, int CH, int B, const float *img, const float *ref, float C1, float C2, int train,
+                        float *ssim_map, float *dm_dmu1, float *dm_dsigma1_sq, float *dm_dsigma12, cudaStream_t s);
+int launch_ssim_backward(int W, int H, int CH, int B, const float *img, const float *ref, const float *dL_dmap,
+                         const float *dm_dmu1, const float *dm_dsigma1_sq, const float *dm_dsigma12, float *dL_dimg,
+                         cudaStream_t s);
+int launch_photometric_loss(int W, int H, int C, const float *image, const float *target, float lambda, float C1,
+                            float C2, float *scratch, double *acc, float *vpixels, float *loss, cudaStream_t s);
+
 // ---- coalesced copy between a contiguous span of `nb` rows of `row` floats in global memory and per-thread padded
 // rows in shared memory (row g at s + g*stride).  128-bit global accesses when `aligned16`; the (row, column)
 // of each quad is advanced incrementally (two integer divisions per thread in total, none in the loop).

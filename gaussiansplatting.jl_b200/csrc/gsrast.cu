@@ -73,6 +73,10 @@ struct GsrHandle {
     int next_slot = 0;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t t_base = nullptr;
+
+    // photometric loss scratch: three (W,H,3) derivative maps + two double accumulators
+    float *loss_maps = nullptr;
+    double *loss_acc = nullptr;
 };
 
 namespace {
@@ -316,6 +320,8 @@ int gsr_destroy(GsrHandle *h) {
     dev_free(h, h->ranges, 2 * (size_t)h->n_tiles);
     dev_free(h, h->n_contrib, px);
     dev_free(h, h->accum_alpha, px);
+    dev_free(h, h->loss_maps, 9 * px);
+    dev_free(h, h->loss_acc, 2);
     if (h->total_host) cudaFreeHost(h->total_host);
     for (cudaEvent_t e : h->ev)
         if (e) cudaEventDestroy(e);
@@ -716,6 +722,55 @@ int gsr_measure_fp32_peak(double *tflops, void *stream) {
     double ms = 0.0, flops = 0.0;
     if (launch_fp32_peak(static_cast<cudaStream_t>(stream), &ms, &flops) != 0) return GSR_ECUDA;
     *tflops = flops / (ms * 1e-3) / 1e12;
+    return GSR_OK;
+}
+
+int gsr_ssim_forward(int32_t width, int32_t height, int32_t channels, int32_t batch, const float *img_dev,
+                     const float *ref_dev, float C1, float C2, int32_t train, float *ssim_map_dev, float *dm_dmu1_dev,
+                     float *dm_dsigma1_sq_dev, float *dm_dsigma12_dev, void *stream) {
+    GsrHandle *h = nullptr;
+    if (width < 0 || height < 0 || channels < 0 || batch < 0 || (int64_t)channels * batch > 65535)
+        return fail(h, GSR_EINVAL, "gsr_ssim_forward: bad shape");
+    if ((int64_t)width * height * channels * batch == 0) return GSR_OK;
+    if (!img_dev || !ref_dev || !ssim_map_dev || (train && (!dm_dmu1_dev || !dm_dsigma1_sq_dev || !dm_dsigma12_dev)))
+        return fail(h, GSR_EINVAL, "gsr_ssim_forward: null argument");
+    if (launch_ssim_forward(width, height, channels, batch, img_dev, ref_dev, C1, C2, train, ssim_map_dev, dm_dmu1_dev,
+                            dm_dsigma1_sq_dev, dm_dsigma12_dev, static_cast<cudaStream_t>(stream)))
+        return cuda_fail(h, cudaGetLastError(), "ssim_fwd_kernel");
+    return GSR_OK;
+}
+
+int gsr_ssim_backward(int32_t width, int32_t height, int32_t channels, int32_t batch, const float *img_dev,
+                      const float *ref_dev, const float *dL_dmap_dev, const float *dm_dmu1_dev,
+                      const float *dm_dsigma1_sq_dev, const float *dm_dsigma12_dev, float *dL_dimg_dev, void *stream) {
+    GsrHandle *h = nullptr;
+    if (width < 0 || height < 0 || channels < 0 || batch < 0 || (int64_t)channels * batch > 65535)
+        return fail(h, GSR_EINVAL, "gsr_ssim_backward: bad shape");
+    if ((int64_t)width * height * channels * batch == 0) return GSR_OK;
+    if (!img_dev || !ref_dev || !dL_dmap_dev || !dm_dmu1_dev || !dm_dsigma1_sq_dev || !dm_dsigma12_dev || !dL_dimg_dev)
+        return fail(h, GSR_EINVAL, "gsr_ssim_backward: null argument");
+    if (launch_ssim_backward(width, height, channels, batch, img_dev, ref_dev, dL_dmap_dev, dm_dmu1_dev,
+                             dm_dsigma1_sq_dev, dm_dsigma12_dev, dL_dimg_dev, static_cast<cudaStream_t>(stream)))
+        return cuda_fail(h, cudaGetLastError(), "ssim_bwd_kernel");
+    return GSR_OK;
+}
+
+int gsr_photometric_loss(GsrHandle *h, const float *image_dev, const float *target_dev, float lambda_dssim,
+                         float *vpixels_dev, float *loss_dev, void *stream) {
+    if (!h) return GSR_EINVAL;
+    if (!image_dev || !target_dev || !vpixels_dev || !loss_dev)
+        return fail(h, GSR_EINVAL, "gsr_photometric_loss: null argument");
+    if (!(lambda_dssim >= 0.f && lambda_dssim <= 1.f)) return fail(h, GSR_EINVAL, "gsr_photometric_loss: lambda outside [0,1]");
+    const size_t px = (size_t)h->cfg.width * h->cfg.height;
+    if (!h->loss_maps) {
+        CK(dev_alloc(h, &h->loss_maps, 9 * px));
+        CK(dev_alloc(h, &h->loss_acc, 2));
+    }
+    // C1, C2: the Float32 keyword defaults of fused_ssim (fused_ssim.jl:391)
+    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    if (launch_photometric_loss(h->cfg.width, h->cfg.height, h->cfg.channels, image_dev, target_dev, lambda_dssim, C1, C2,
+                                h->loss_maps, h->loss_acc, vpixels_dev, loss_dev, static_cast<cudaStream_t>(stream)))
+        return cuda_fail(h, cudaGetLastError(), "photometric loss");
     return GSR_OK;
 }
 

@@ -190,6 +190,30 @@ GSR_API int gsr_identify_tile_range(const uint64_t *keys_dev, int64_t m, uint32_
 GSR_API int gsr_sort_pairs(GsrHandle *h, const uint64_t *keys_in_dev, const uint32_t *vals_in_dev, int64_t m,
                    uint64_t *keys_out_dev, uint32_t *vals_out_dev, void *stream);
 
+/* ---- the loss either side of the path ------------------------------------------------
+ * Fused SSIM.  Arrays are the reference's (W,H,CH,B) column-major Float32, i.e. planar [b][c][y][x]; any W, H
+ * (zero padding outside the image, 11-tap sigma=1.5 window).  No handle: stateless, errors via the return code
+ * and gsr_last_error(NULL). */
+/* `_fused_ssim(img; ref, C1, C2, train)` — fused_ssim.jl:354-372 (kernel :34-258).  Writes ssim_map and, when
+ * train != 0, the three partial-derivative maps the pullback needs (pass NULL for them otherwise). */
+GSR_API int gsr_ssim_forward(int32_t width, int32_t height, int32_t channels, int32_t batch, const float *img_dev,
+                             const float *ref_dev, float C1, float C2, int32_t train, float *ssim_map_dev,
+                             float *dm_dmu1_dev, float *dm_dsigma1_sq_dev, float *dm_dsigma12_dev, void *stream);
+/* `fused_ssim_bwd(img, ref, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12)` — fused_ssim.jl:374-389 (kernel
+ * :261-352), the pullback of the rrule at :397-407.  Every element of dL_dimg is written. */
+GSR_API int gsr_ssim_backward(int32_t width, int32_t height, int32_t channels, int32_t batch, const float *img_dev,
+                              const float *ref_dev, const float *dL_dmap_dev, const float *dm_dmu1_dev,
+                              const float *dm_dsigma1_sq_dev, const float *dm_dsigma12_dev, float *dL_dimg_dev,
+                              void *stream);
+/* The photometric loss of Trainer.step! (training.jl:684-699) and its pullback to the raster image in one call:
+ *   x = image[1:3,:,:] ; total = (1-lambda)*mean|x - target| + lambda*(1 - mean(fused_ssim(x; ref=target)))
+ * image_dev / vpixels_dev: the handle's (C,W,H) raster image / its cotangent (channels >= 3 get zeros), consumed
+ * and produced in place of the slice / permutedims / reshape passes and their pullbacks; target_dev: (W,H,3).
+ * loss_dev: 3 floats {total, mean|x - t|, mean ssim} written on the stream (read them when convenient).
+ * vpixels_dev feeds gsr_backward directly.  Scratch (three W*H*3 maps) lives in the handle. */
+GSR_API int gsr_photometric_loss(GsrHandle *h, const float *image_dev, const float *target_dev, float lambda_dssim,
+                                 float *vpixels_dev, float *loss_dev, void *stream);
+
 /* Per-stage device timing (CUDA events on the caller's stream; SURVEY.md §5 "tracing / profiling").
  * When enabled, gsr_forward / gsr_backward bracket each stage with events; gsr_profile_get synchronises on
  * them and returns the durations of the last forward + backward in milliseconds (0 for stages that did not run). */

@@ -279,7 +279,7 @@ class Oracle:
                                   self.p(max_radii), self.p(accum), self.p(denom))
 
     # ------------------------------------------------- fused SSIM (§8f-2)
-    def fused_ssim(self, img, ref, C1=0.01 ** 2, C2=0.03 ** 2, train=True):
+    def fused_ssim(self, img, ref, C1=None, C2=None, train=True):
         """`_fused_ssim` — fused_ssim.jl:354-372.  img/ref: (B,CH,H,W) C-contiguous == the reference's (W,H,CH,B).
         Returns (ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12); the last three are None when train is False."""
         img, ref = self.arr(img), self.arr(ref)
@@ -287,7 +287,9 @@ class Oracle:
         assert ref.shape == img.shape
         out = np.zeros_like(img)
         d = [np.zeros_like(img) for _ in range(3)] if train else [None, None, None]
-        c1, c2 = float(np.float32(C1)), float(np.float32(C2))  # Float32 keyword defaults of the reference
+        # Float32 keyword defaults of the reference: 0.01f0^2, 0.03f0^2 (products formed in Float32)
+        c1 = float(np.float32(0.01) * np.float32(0.01)) if C1 is None else float(np.float32(C1))
+        c2 = float(np.float32(0.03) * np.float32(0.03)) if C2 is None else float(np.float32(C2))
         self.lib.orc_fused_ssim(C.c_int32(W), C.c_int32(H), C.c_int32(CH), C.c_int32(B), self.p(img), self.p(ref),
                                 self.r(c1), self.r(c2), C.c_int(1 if train else 0), self.p(out), self.p(d[0]),
                                 self.p(d[1]), self.p(d[2]))

@@ -9,8 +9,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-from oracle import Oracle  # noqa: E402
+from oracle.oracle import Oracle  # noqa: E402
 
 
 def conv_ssim_mean(x, ref, c1=0.01 ** 2, c2=0.03 ** 2):
