@@ -71,7 +71,7 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
                           const float *__restrict__ opac, const float *__restrict__ scales, const float *__restrict__ rots, const GeomPtrs g,
                           float *__restrict__ vmeans, float *__restrict__ vshs, float *__restrict__ vopac,
                           float *__restrict__ vscales, float *__restrict__ vrot, float *vR_out, float *vt_out,
-                          const int sh_stride) {
+                          const int sh_stride, const ParamSpec ps) {
     // SH coefficients in / SH gradients out are staged through shared memory: the (3,K,n) rows of a CTA's
     // 128 Gaussians form one contiguous span that is read and written with coalesced 128-bit accesses, while each
     // thread works on its own padded (odd stride -> conflict-free) row.
@@ -91,10 +91,23 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
     const bool aligned16 = (((uintptr_t)shs | (uintptr_t)vshs) & 15) == 0;
     if (__syncthreads_or(visible_t) && sh_degree > 0) {
         if (k_used == K) {
-            rows_global_to_shared(shs + block0 * row, s_sh, (int)nb, row, sh_stride, tid, BG_THREADS, aligned16);
+            if (ps.sh_rest) {
+                rows_global_to_shared(shs + block0 * 3, s_sh, (int)nb, 3, sh_stride, tid, BG_THREADS, false);
+                if (K > 1)
+                    rows_global_to_shared(ps.sh_rest + block0 * (int64_t)(row - 3), s_sh + 3, (int)nb, row - 3, sh_stride, tid,
+                                          BG_THREADS, (reinterpret_cast<uintptr_t>(ps.sh_rest) & 15) == 0);
+            } else {
+                rows_global_to_shared(shs + block0 * row, s_sh, (int)nb, row, sh_stride, tid, BG_THREADS, aligned16);
+            }
         } else if (visible_t) {
-            const float *src = shs + i * (int64_t)row;
-            for (int e = 0; e < 3 * k_used; e++) s_sh[tid * sh_stride + e] = src[e];
+            if (ps.sh_rest) {
+                for (int e = 0; e < 3; e++) s_sh[tid * sh_stride + e] = shs[3 * i + e];
+                const float *src = ps.sh_rest + i * (int64_t)(row - 3);
+                for (int e = 3; e < 3 * k_used; e++) s_sh[tid * sh_stride + e] = src[e - 3];
+            } else {
+                const float *src = shs + i * (int64_t)row;
+                for (int e = 0; e < 3 * k_used; e++) s_sh[tid * sh_stride + e] = src[e];
+            }
         }
     }
     __syncthreads();
@@ -109,7 +122,11 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
             g.grad_means2d[i] = make_float2(0.f, 0.f);
             if (!ACC) {
 #pragma unroll
-                for (int k = 0; k < 3; k++) { vmeans[3 * i + k] = 0.f; vscales[3 * i + k] = 0.f; }
+                for (int k = 0; k < 3; k++) vmeans[3 * i + k] = 0.f;
+                if (ps.isotropic) vscales[i] = 0.f;
+                else
+#pragma unroll
+                    for (int k = 0; k < 3; k++) vscales[3 * i + k] = 0.f;
                 *reinterpret_cast<float4 *>(vrot + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
                 vopac[i] = 0.f;
             }
@@ -126,8 +143,9 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
             const float ca = g.conics[3 * i], cb = g.conics[3 * i + 1], cc = g.conics[3 * i + 2];
             const float vm2[2] = {ca * a0.x + cb * a0.y, cb * a0.x + cc * a0.y};
             const float vcn[3] = {0.5f * a0.z, 0.5f * a0.w, 0.5f * a1.x};
-            const float op = opac[i];
-            const float vop = op > 0.0f ? a1.y / op : 0.0f;
+            const float op = ps.raw_opacity ? act_sigmoid(opac[i]) : opac[i];
+            float vop = op > 0.0f ? a1.y / op : 0.0f;
+            if (ps.raw_opacity) vop *= op * (1.0f - op);  // pullback of sigmoid (rasterizer.jl:229)
             float vcol[8] = {a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, 0.f, 0.f};
             if (channels > 5) {
                 const float4 a3 = *reinterpret_cast<const float4 *>(acc + 12);
@@ -149,7 +167,13 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
                 for (int k = 0; k < 3; k++) t[k] = cam.t[k];
             }
             const float mean[3] = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
-            const float sc[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
+            float sc[3];
+            if (ps.isotropic) {
+                sc[0] = sc[1] = sc[2] = expf(scales[i]);
+            } else {
+                sc[0] = scales[3 * i]; sc[1] = scales[3 * i + 1]; sc[2] = scales[3 * i + 2];
+                if (ps.raw_scale) { sc[0] = expf(sc[0]); sc[1] = expf(sc[1]); sc[2] = expf(sc[2]); }
+            }
             const float4 q4 = *reinterpret_cast<const float4 *>(rots + 4 * i);
 
             // ∇inverse (render.jl:383-385): vΣ2D = -Σ⁻¹ vΣ⁻¹ Σ⁻¹ with symmetric 2x2 operands (projection.jl:178-188)
@@ -391,7 +415,17 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
             }
 
 #pragma unroll
-            for (int k = 0; k < 3; k++) { put<ACC>(vmeans + 3 * i + k, vmean[k]); put<ACC>(vscales + 3 * i + k, vscale[k]); }
+            for (int k = 0; k < 3; k++) put<ACC>(vmeans + 3 * i + k, vmean[k]);
+            if (ps.raw_scale || ps.isotropic) {  // pullback of exp: d exp(s) = exp(s) ds (rasterizer.jl:237)
+#pragma unroll
+                for (int k = 0; k < 3; k++) vscale[k] *= sc[k];
+            }
+            if (ps.isotropic) {
+                put<ACC>(vscales + i, (vscale[0] + vscale[1]) + vscale[2]);  // pullback of vcat(s, s, s)
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; k++) put<ACC>(vscales + 3 * i + k, vscale[k]);
+            }
             if (ACC) {
                 float4 o = *reinterpret_cast<float4 *>(vrot + 4 * i);
                 o.x += vq[0]; o.y += vq[1]; o.z += vq[2]; o.w += vq[3];
@@ -405,7 +439,14 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
     // coalesced write-out of the CTA's SH-gradient span
     __syncthreads();
     {
-        rows_shared_to_global<ACC>(vshs + block0 * row, s_sh, (int)nb, row, sh_stride, tid, BG_THREADS, aligned16);
+        if (ps.sh_rest) {
+            rows_shared_to_global<ACC>(vshs + block0 * 3, s_sh, (int)nb, 3, sh_stride, tid, BG_THREADS, false);
+            if (K > 1)
+                rows_shared_to_global<ACC>(ps.vsh_rest + block0 * (int64_t)(row - 3), s_sh + 3, (int)nb, row - 3, sh_stride, tid,
+                                           BG_THREADS, (reinterpret_cast<uintptr_t>(ps.vsh_rest) & 15) == 0);
+        } else {
+            rows_shared_to_global<ACC>(vshs + block0 * row, s_sh, (int)nb, row, sh_stride, tid, BG_THREADS, aligned16);
+        }
     }
 
     if (pose) {  // CTA-level reduction of the 12 pose cotangents before one atomic each (TODO at projection.jl:242)
@@ -491,7 +532,7 @@ void launch_backward_gaussians(const DevCamera &cam, int64_t n, int sh_degree, i
                                const float *means, const float *shs, const float *opac, const float *scales,
                                const float *rots,
                                const GeomPtrs &g, float *vmeans, float *vshs, float *vopac, float *vscales,
-                               float *vrot, float *vR, float *vt, int accumulate, cudaStream_t s) {
+                               float *vrot, float *vR, float *vt, int accumulate, cudaStream_t s, const ParamSpec &ps) {
     if (n <= 0) return;
     const unsigned blocks = (unsigned)((n + BG_THREADS - 1) / BG_THREADS);
     int stride = 3 * K;
@@ -500,11 +541,11 @@ void launch_backward_gaussians(const DevCamera &cam, int64_t n, int sh_degree, i
     if (accumulate)
         backward_gaussians_kernel<true><<<blocks, BG_THREADS, smem, s>>>(cam, n, sh_degree, K, channels, means, shs, opac,
                                                                         scales, rots, g, vmeans, vshs, vopac, vscales,
-                                                                        vrot, vR, vt, stride);
+                                                                        vrot, vR, vt, stride, ps);
     else
         backward_gaussians_kernel<false><<<blocks, BG_THREADS, smem, s>>>(cam, n, sh_degree, K, channels, means, shs, opac,
                                                                          scales, rots, g, vmeans, vshs, vopac, vscales,
-                                                                         vrot, vR, vt, stride);
+                                                                         vrot, vR, vt, stride, ps);
     count_launch();
 }
 

@@ -49,9 +49,20 @@ struct GeomPtrs {  // GeometryState (states.jl:2-47), SoA
 };
 
 // ---- launchers (one per translation unit) ---------------------------------------------------------------
+// How the caller's parameter arrays are to be read (the activation pre-pass of the functor,
+// rasterizer.jl:217-248, folded into the kernels).  All-zero = activated inputs, one (3,K,N) SH array.
+struct ParamSpec {
+    int raw_opacity = 0;            // opacities are pre-sigmoid (NU.sigmoid, rasterizer.jl:229)
+    int raw_scale = 0;              // scales are log-scales (exp, rasterizer.jl:237)
+    int isotropic = 0;              // scales is (1,N), broadcast to the three axes (rasterizer.jl:236,240-243)
+    const float *sh_rest = nullptr; // non-null: `shs` is features_dc (3,1,N) and this features_rest (3,K-1,N) (hcat, :218)
+    float *vsh_rest = nullptr;      // backward: cotangent of sh_rest
+};
+__device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
 void launch_preprocess(const DevCamera &cam, int64_t n, int sh_degree, int K, int channels, const float *means,
                        const float *shs, const float *opac, const float *scales, const float *rots,
-                       const GeomPtrs &g, cudaStream_t s);
+                       const GeomPtrs &g, cudaStream_t s, const ParamSpec &ps = ParamSpec());
 
 void launch_scan_tiles(int64_t n, const int32_t *tiles_touched, int32_t *points_offset, uint32_t *scan_state,
                        int64_t *total_dev, cudaStream_t s);
@@ -87,7 +98,8 @@ void launch_backward_gaussians(const DevCamera &cam, int64_t n, int sh_degree, i
                                const float *means, const float *shs, const float *opac, const float *scales,
                                const float *rots,
                                const GeomPtrs &g, float *vmeans, float *vshs, float *vopac, float *vscales,
-                               float *vrot, float *vR, float *vt, int accumulate, cudaStream_t s);
+                               float *vrot, float *vR, float *vt, int accumulate, cudaStream_t s,
+                               const ParamSpec &ps = ParamSpec());
 
 void launch_update_stats(int64_t n, const int32_t *radii, const float2 *grad_means2d, uint32_t width,
                          uint32_t height, int32_t *max_radii, float *accum, float *denom, cudaStream_t s);

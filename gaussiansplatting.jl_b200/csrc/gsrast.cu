@@ -365,10 +365,10 @@ int gsr_get_state(const GsrHandle *h, GsrStateViews *v) {
     return GSR_OK;
 }
 
-int gsr_forward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K, const float *means,
-                const float *shs, const float *opacities, const float *scales, const float *rotations,
-                const float background[3], float *image_out, uint8_t *covis, float *uncert, int64_t *n_rendered,
-                void *stream) {
+static int forward_impl(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K, const float *means,
+                        const float *shs, const float *opacities, const float *scales, const float *rotations,
+                        const float background[3], float *image_out, uint8_t *covis, float *uncert, int64_t *n_rendered,
+                        void *stream, const ParamSpec &ps) {
     if (!h) return GSR_EINVAL;
     if (!cam || !image_out || !background) return fail(h, GSR_EINVAL, "gsr_forward: null argument");
     if (n < 0 || sh_degree < 0 || sh_degree > 3 || K < (sh_degree + 1) * (sh_degree + 1))
@@ -394,7 +394,7 @@ int gsr_forward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree
     if (n > 0) {
         {
             StageTimer tm(h, s, GSR_STAGE_PREPROCESS);
-            launch_preprocess(dc, n, sh_degree, K, ch, means, shs, opacities, scales, rotations, h->g, s);
+            launch_preprocess(dc, n, sh_degree, K, ch, means, shs, opacities, scales, rotations, h->g, s, ps);
         }
         {
             StageTimer tm(h, s, GSR_STAGE_SCAN);
@@ -442,10 +442,46 @@ int gsr_forward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree
     return GSR_OK;
 }
 
-int gsr_backward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K, const float *means,
-                 const float *shs, const float *opacities, const float *scales, const float *rotations,
-                 const float background[3], const float *vpixels, float *vmeans, float *vshs, float *vopacities,
-                 float *vscales, float *vrot, float *vR, float *vt, int32_t accumulate, void *stream) {
+int gsr_forward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K, const float *means,
+                const float *shs, const float *opacities, const float *scales, const float *rotations,
+                const float background[3], float *image_out, uint8_t *covis, float *uncert, int64_t *n_rendered,
+                void *stream) {
+    return forward_impl(h, cam, n, sh_degree, K, means, shs, opacities, scales, rotations, background, image_out, covis,
+                        uncert, n_rendered, stream, ParamSpec());
+}
+
+static int raw_spec(GsrHandle *h, int32_t K, const float *features_rest, float *vfeatures_rest, bool backward,
+                    int32_t isotropic, ParamSpec *ps) {
+    static const float dummy_rest = 0.f;
+    static float dummy_vrest = 0.f;
+    if (K > 1 && (!features_rest || (backward && !vfeatures_rest)))
+        return fail(h, GSR_EINVAL, "raw parameters: features_rest (and its cotangent) required when K > 1");
+    ps->raw_opacity = 1;
+    ps->raw_scale = 1;
+    ps->isotropic = isotropic ? 1 : 0;
+    // K == 1: no remainder coefficients; a non-null tag still selects the split layout (it is never dereferenced)
+    ps->sh_rest = features_rest ? features_rest : &dummy_rest;
+    ps->vsh_rest = vfeatures_rest ? vfeatures_rest : &dummy_vrest;
+    return GSR_OK;
+}
+
+int gsr_forward_raw(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K, const float *means,
+                    const float *features_dc, const float *features_rest, const float *opacities_raw,
+                    const float *scales_raw, int32_t isotropic, const float *rotations, const float background[3],
+                    float *image_out, uint8_t *covis, float *uncert, int64_t *n_rendered, void *stream) {
+    if (!h) return GSR_EINVAL;
+    ParamSpec ps;
+    int rc = raw_spec(h, K, features_rest, nullptr, false, isotropic, &ps);
+    if (rc) return rc;
+    return forward_impl(h, cam, n, sh_degree, K, means, features_dc, opacities_raw, scales_raw, rotations, background,
+                        image_out, covis, uncert, n_rendered, stream, ps);
+}
+
+static int backward_impl(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K, const float *means,
+                         const float *shs, const float *opacities, const float *scales, const float *rotations,
+                         const float background[3], const float *vpixels, float *vmeans, float *vshs, float *vopacities,
+                         float *vscales, float *vrot, float *vR, float *vt, int32_t accumulate, void *stream,
+                         const ParamSpec &ps) {
     if (!h) return GSR_EINVAL;
     if (!cam || !background || !vpixels || !vmeans || !vshs || !vopacities || !vscales || !vrot || !opacities)
         return fail(h, GSR_EINVAL, "gsr_backward: null argument");
@@ -474,10 +510,32 @@ int gsr_backward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degre
     {
         StageTimer tm(h, s, GSR_STAGE_GAUSS_BWD);
         launch_backward_gaussians(dc, n, sh_degree, K, ch, means, shs, opacities, scales, rotations, h->g, vmeans,
-                                  vshs, vopacities, vscales, vrot, vR, vt, accumulate, s);
+                                  vshs, vopacities, vscales, vrot, vR, vt, accumulate, s, ps);
     }
     CK(cudaGetLastError());
     return GSR_OK;
+}
+
+int gsr_backward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K, const float *means,
+                 const float *shs, const float *opacities, const float *scales, const float *rotations,
+                 const float background[3], const float *vpixels, float *vmeans, float *vshs, float *vopacities,
+                 float *vscales, float *vrot, float *vR, float *vt, int32_t accumulate, void *stream) {
+    return backward_impl(h, cam, n, sh_degree, K, means, shs, opacities, scales, rotations, background, vpixels, vmeans,
+                         vshs, vopacities, vscales, vrot, vR, vt, accumulate, stream, ParamSpec());
+}
+
+int gsr_backward_raw(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K, const float *means,
+                     const float *features_dc, const float *features_rest, const float *opacities_raw,
+                     const float *scales_raw, int32_t isotropic, const float *rotations, const float background[3],
+                     const float *vpixels, float *vmeans, float *vfeatures_dc, float *vfeatures_rest,
+                     float *vopacities_raw, float *vscales_raw, float *vrot, float *vR, float *vt, int32_t accumulate,
+                     void *stream) {
+    if (!h) return GSR_EINVAL;
+    ParamSpec ps;
+    int rc = raw_spec(h, K, features_rest, vfeatures_rest, true, isotropic, &ps);
+    if (rc) return rc;
+    return backward_impl(h, cam, n, sh_degree, K, means, features_dc, opacities_raw, scales_raw, rotations, background,
+                         vpixels, vmeans, vfeatures_dc, vopacities_raw, vscales_raw, vrot, vR, vt, accumulate, stream, ps);
 }
 
 int gsr_set_accumulator(GsrHandle *h, float *gacc_dev, int64_t capacity_gaussians) {

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(PP_THREADS, 8)
 preprocess_kernel(const DevCamera cam, const int64_t n, const int sh_degree, const int K, const int channels,
                   const float *__restrict__ means, const float *__restrict__ shs, const float *__restrict__ opac,
                   const float *__restrict__ scales, const float *__restrict__ rots, const GeomPtrs g,
-                  const int sh_stride) {
+                  const int sh_stride, const ParamSpec ps) {
     extern __shared__ float s_sh[];  // [PP_THREADS][sh_stride]
     const int tid = threadIdx.x;
     const int64_t block0 = (int64_t)blockIdx.x * PP_THREADS;
@@ -89,7 +89,13 @@ preprocess_kernel(const DevCamera cam, const int64_t n, const int sh_degree, con
         for (int r = 0; r < 3; r++) mc[r] = ((R[r] * mean[0] + R[r + 3] * mean[1]) + R[r + 6] * mean[2]) + t[r];
         if (cam.near_plane < mc[2] && mc[2] < cam.far_plane) {  // projection.jl:79
             const float4 q4 = *reinterpret_cast<const float4 *>(rots + 4 * i);  // 128-bit load (simd.jl:1-11)
-            const float sc[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
+            float sc[3];
+            if (ps.isotropic) {
+                sc[0] = sc[1] = sc[2] = expf(scales[i]);  // rasterizer.jl:240-243
+            } else {
+                sc[0] = scales[3 * i]; sc[1] = scales[3 * i + 1]; sc[2] = scales[3 * i + 2];
+                if (ps.raw_scale) { sc[0] = expf(sc[0]); sc[1] = expf(sc[1]); sc[2] = expf(sc[2]); }
+            }
             // unnorm_quat2rot (render.jl:322-333): normalize(q) = inv(norm(q)) * q
             const float qn = sqrtf(((q4.x * q4.x + q4.y * q4.y) + q4.z * q4.z) + q4.w * q4.w);
             const float qi = 1.0f / qn;
@@ -180,10 +186,23 @@ preprocess_kernel(const DevCamera cam, const int64_t n, const int sh_degree, con
     if (any_visible) {
         if (k_used == K) {
             const int nb = (int)((n - block0) < PP_THREADS ? (n - block0) : PP_THREADS);
-            rows_global_to_shared(shs + block0 * (int64_t)(3 * K), s_sh, nb, 3 * K, sh_stride, tid, PP_THREADS, ALIGNED16);
+            if (ps.sh_rest) {  // features_dc | features_rest kept apart by the caller: same rows, two spans
+                rows_global_to_shared(shs + block0 * 3, s_sh, nb, 3, sh_stride, tid, PP_THREADS, false);
+                if (K > 1)
+                    rows_global_to_shared(ps.sh_rest + block0 * (int64_t)(3 * (K - 1)), s_sh + 3, nb, 3 * (K - 1), sh_stride, tid,
+                                          PP_THREADS, (reinterpret_cast<uintptr_t>(ps.sh_rest) & 15) == 0);
+            } else {
+                rows_global_to_shared(shs + block0 * (int64_t)(3 * K), s_sh, nb, 3 * K, sh_stride, tid, PP_THREADS, ALIGNED16);
+            }
         } else if (visible) {  // k_used < K: only the leading coefficients are needed — direct strided loads
-            const float *src = shs + i * (int64_t)(3 * K);
-            for (int e = 0; e < 3 * k_used; e++) s_sh[tid * sh_stride + e] = src[e];
+            if (ps.sh_rest) {
+                for (int e = 0; e < 3; e++) s_sh[tid * sh_stride + e] = shs[3 * i + e];
+                const float *src = ps.sh_rest + i * (int64_t)(3 * (K - 1));
+                for (int e = 3; e < 3 * k_used; e++) s_sh[tid * sh_stride + e] = src[e - 3];
+            } else {
+                const float *src = shs + i * (int64_t)(3 * K);
+                for (int e = 0; e < 3 * k_used; e++) s_sh[tid * sh_stride + e] = src[e];
+            }
         }
     }
     __syncthreads();
@@ -249,7 +268,7 @@ preprocess_kernel(const DevCamera cam, const int64_t n, const int sh_degree, con
     if (channels > 5) { g.normals[3 * i] = nrm[0]; g.normals[3 * i + 1] = nrm[1]; g.normals[3 * i + 2] = nrm[2]; }
 
     // packed record for the compositing kernels; features = rgb, depth, 1, normal (rasterizer.jl:380-386)
-    const float o = opac[i];
+    const float o = ps.raw_opacity ? act_sigmoid(opac[i]) : opac[i];
     const int RQ = rec_quads(channels);
     float4 *rec = g.rec + i * RQ;
     rec[0] = make_float4(m2[0], m2[1], conic[0], conic[1]);
@@ -266,7 +285,7 @@ preprocess_kernel(const DevCamera cam, const int64_t n, const int sh_degree, con
 
 void launch_preprocess(const DevCamera &cam, int64_t n, int sh_degree, int K, int channels, const float *means,
                        const float *shs, const float *opac, const float *scales, const float *rots,
-                       const GeomPtrs &g, cudaStream_t s) {
+                       const GeomPtrs &g, cudaStream_t s, const ParamSpec &ps) {
     if (n <= 0) return;
     int stride = 3 * K;
     if ((stride & 1) == 0) stride += 1;  // odd row stride: conflict-free per-thread reads
@@ -275,9 +294,9 @@ void launch_preprocess(const DevCamera &cam, int64_t n, int sh_degree, int K, in
     const bool aligned = (reinterpret_cast<uintptr_t>(shs) & 15) == 0;
     if (aligned)
         preprocess_kernel<true><<<(unsigned)blocks, PP_THREADS, smem, s>>>(cam, n, sh_degree, K, channels, means, shs,
-                                                                          opac, scales, rots, g, stride);
+                                                                          opac, scales, rots, g, stride, ps);
     else
         preprocess_kernel<false><<<(unsigned)blocks, PP_THREADS, smem, s>>>(cam, n, sh_degree, K, channels, means,
-                                                                           shs, opac, scales, rots, g, stride);
+                                                                           shs, opac, scales, rots, g, stride, ps);
     count_launch();
 }

@@ -40,7 +40,7 @@ EXPORTS = ["gsr_version", "gsr_last_error", "gsr_create", "gsr_destroy", "gsr_re
            "gsr_forward_backward_host", "gsr_identify_tile_range", "gsr_sort_pairs", "gsr_launch_count",
            "gsr_profile_enable", "gsr_profile_get", "gsr_measure_fp32_peak", "gsr_forward_backward_host_async",
            "gsr_host_wait", "gsr_host_timeline", "gsr_set_accumulator", "gsr_backward_render",
-           "gsr_backward_gaussians_peers", "gsr_ssim_forward", "gsr_ssim_backward", "gsr_photometric_loss"]
+           "gsr_backward_gaussians_peers", "gsr_ssim_forward", "gsr_ssim_backward", "gsr_photometric_loss", "gsr_forward_raw", "gsr_backward_raw"]
 STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "render_fwd", "zero_grads", "render_bwd", "gauss_bwd"]
 
 
@@ -75,6 +75,10 @@ def load() -> C.CDLL:
     lib.gsr_backward.argtypes = [vp, C.POINTER(GsrCamera), i64, i32, i32, vp, vp, vp, vp, vp, C.POINTER(C.c_float),
                                  vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.gsr_update_stats.argtypes = [vp, i64, vp, vp, vp, vp]
+    lib.gsr_forward_raw.argtypes = [vp, C.POINTER(GsrCamera), i64, i32, i32, vp, vp, vp, vp, vp, i32, vp,
+                                    C.POINTER(C.c_float), vp, vp, vp, C.POINTER(i64), vp]
+    lib.gsr_backward_raw.argtypes = [vp, C.POINTER(GsrCamera), i64, i32, i32, vp, vp, vp, vp, vp, i32, vp,
+                                     C.POINTER(C.c_float), vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.gsr_forward_backward_host.argtypes = [vp, C.POINTER(GsrCamera), i64, i32, i32, vp, vp, vp, vp, vp,
                                               C.POINTER(C.c_float), vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), vp]
     lib.gsr_forward_backward_host_async.argtypes = lib.gsr_forward_backward_host.argtypes

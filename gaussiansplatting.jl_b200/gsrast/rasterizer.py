@@ -163,7 +163,16 @@ class GaussianRasterizer:
     # ---- functor: activation pre-pass + rasterize (rasterizer.jl:200-253) ---------------------------------
     def __call__(self, means_3d, opacities, scales, rotations, sh_color, sh_remainder, R_w2c=None, t_w2c=None, *,
                  camera: Camera, sh_degree: int, background=(0.0, 0.0, 0.0), covisibilities=None,
-                 uncertainties=None):
+                 uncertainties=None, fused_activations: bool = True):
+        """Raw parameters in (pre-sigmoid opacities, log-scales (N,3) or isotropic (N,1), features_dc | features_rest).
+
+        fused_activations=True (default): one library call each way — sigmoid / exp / the SH concatenation and their
+        pullbacks run inside the per-Gaussian kernels (gsr_forward_raw / gsr_backward_raw).  False: the reference's
+        own composition — torch broadcasts, then `rasterize` on the activated arrays (autograd chains the pullbacks)."""
+        if fused_activations:
+            rest = None if sh_remainder is None or sh_remainder.numel() == 0 else sh_remainder
+            return _RasterizeRaw.apply(means_3d, opacities, scales, rotations, sh_color, rest, R_w2c, t_w2c, self, camera,
+                                       int(sh_degree), tuple(float(b) for b in background), covisibilities, uncertainties)
         shs = sh_color if sh_remainder is None or sh_remainder.numel() == 0 else torch.cat([sh_color, sh_remainder], 1)
         opacities_act = torch.sigmoid(opacities)
         if scales.shape[1] == 1:  # isotropic (rasterizer.jl:235-244)
@@ -172,6 +181,41 @@ class GaussianRasterizer:
         return rasterize(means_3d, shs, opacities_act, scales_act, rotations, R_w2c, t_w2c, rast=self, camera=camera,
                          sh_degree=sh_degree, background=background, covisibilities=covisibilities,
                          uncertainties=uncertainties)
+
+    def _raw_call(self, backward, means, opac, scales, rots, dc, rest, R_w2c, t_w2c, camera, sh_degree, background,
+                  image=None, covis=None, uncert=None, vpixels=None, outs=None, accumulate=False):
+        assert camera.width == self.width and camera.height == self.height
+        n = means.shape[0]
+        K = 1 + (0 if rest is None else rest.shape[1])
+        iso = int(scales.shape[1] == 1)
+        cam = camera.to_c(_ptr(R_w2c), _ptr(t_w2c))
+        bg = (C.c_float * 3)(*[float(b) for b in background])
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            if not backward:
+                m = C.c_int64(0)
+                check(_lib.lib().gsr_forward_raw(self._h, C.byref(cam), n, sh_degree, K, _ptr(means), _ptr(dc), _ptr(rest),
+                                                 _ptr(opac), _ptr(scales), iso, _ptr(rots), bg, _ptr(image), _ptr(covis),
+                                                 _ptr(uncert), C.byref(m), stream), self._h)
+                self.n_rendered = int(m.value)
+                return image
+            dev = self.device
+            if outs is None:
+                outs = dict(vmeans=torch.empty((n, 3), device=dev), vfeatures_dc=torch.empty((n, 1, 3), device=dev),
+                            vfeatures_rest=None if rest is None else torch.empty((n, K - 1, 3), device=dev),
+                            vopacities=torch.empty((n, 1), device=dev), vscales=torch.empty_like(scales),
+                            vrot=torch.empty((n, 4), device=dev))
+            vR = vt = None
+            if R_w2c is not None:
+                vR, vt = torch.zeros((3, 3), device=dev), torch.zeros(3, device=dev)
+            check(_lib.lib().gsr_backward_raw(self._h, C.byref(cam), n, sh_degree, K, _ptr(means), _ptr(dc), _ptr(rest),
+                                              _ptr(opac), _ptr(scales), iso, _ptr(rots), bg, _ptr(vpixels),
+                                              _ptr(outs["vmeans"]), _ptr(outs["vfeatures_dc"]), _ptr(outs["vfeatures_rest"]),
+                                              _ptr(outs["vopacities"]), _ptr(outs["vscales"]), _ptr(outs["vrot"]), _ptr(vR),
+                                              _ptr(vt), int(bool(accumulate)), stream), self._h)
+            outs["vR"] = None if vR is None else vR.t()
+            outs["vt"] = vt
+            return outs
 
     # ---- raw stages ------------------------------------------------------------------------------------------
     def _forward(self, means, shs, opac, scales, rots, R_w2c, t_w2c, camera, sh_degree, background, covis, uncert,
@@ -308,6 +352,34 @@ class _Rasterize(torch.autograd.Function):
                                ctx.background)
         return (g["vmeans"], g["vshs"], g["vopacities"].view_as(opac), g["vscales"], g["vrot"], g["vR"], g["vt"],
                 None, None, None, None, None, None)
+
+
+class _RasterizeRaw(torch.autograd.Function):
+    """The functor of rasterizer.jl:200-253 as ONE differentiable operator on the raw parameters."""
+
+    @staticmethod
+    def forward(ctx, means, opac, scales, rots, dc, rest, R_w2c, t_w2c, rast, camera, sh_degree, background, covis,
+                uncert):
+        means, opac, scales = _f32c(means, "means_3d"), _f32c(opac, "opacities"), _f32c(scales, "scales")
+        rots, dc = _f32c(rots, "rotations"), _f32c(dc, "sh_color")
+        rest = None if rest is None else _f32c(rest, "sh_remainder")
+        Rc = None if R_w2c is None else _f32c(R_w2c, "R_w2c").t().contiguous()
+        tc = None if t_w2c is None else _f32c(t_w2c, "t_w2c")
+        out = torch.empty((rast.height, rast.width, rast.channels), dtype=torch.float32, device=rast.device)
+        image = rast._raw_call(False, means, opac, scales, rots, dc, rest, Rc, tc, camera, sh_degree, background,
+                               image=out, covis=covis, uncert=uncert)
+        rast.image = image
+        ctx.save_for_backward(means, opac, scales, rots, dc, rest, Rc, tc)
+        ctx.rast, ctx.camera, ctx.sh_degree, ctx.background = rast, camera, sh_degree, background
+        return image
+
+    @staticmethod
+    def backward(ctx, vpixels):
+        means, opac, scales, rots, dc, rest, Rc, tc = ctx.saved_tensors
+        g = ctx.rast._raw_call(True, means, opac, scales, rots, dc, rest, Rc, tc, ctx.camera, ctx.sh_degree,
+                               ctx.background, vpixels=vpixels.contiguous())
+        return (g["vmeans"], g["vopacities"].view_as(opac), g["vscales"], g["vrot"], g["vfeatures_dc"],
+                g["vfeatures_rest"], g["vR"], g["vt"], None, None, None, None, None, None)
 
 
 def rasterize(means_3d, shs, opacities, scales, rotations, R_w2c=None, t_w2c=None, *, rast: GaussianRasterizer,

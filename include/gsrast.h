@@ -190,6 +190,28 @@ GSR_API int gsr_identify_tile_range(const uint64_t *keys_dev, int64_t m, uint32_
 GSR_API int gsr_sort_pairs(GsrHandle *h, const uint64_t *keys_in_dev, const uint32_t *vals_in_dev, int64_t m,
                    uint64_t *keys_out_dev, uint32_t *vals_out_dev, void *stream);
 
+/* ---- the activation pre-pass folded into the path ------------------------------------
+ * The functor `rast(means_3d, opacities, scales, rotations, sh_color, sh_remainder; ...)` — rasterizer.jl:200-253 —
+ * concatenates features_dc | features_rest into (3,K,N), applies NU.sigmoid to the opacities and exp to the
+ * (3,N) or isotropic (1,N) log-scales, then calls `rasterize`; Zygote differentiates those broadcasts.  These two
+ * entry points take the RAW parameters and return RAW-parameter cotangents: the activations are evaluated on load
+ * inside the per-Gaussian kernels (sigmoid(x) = 1/(1+exp(-x)), exp = expf) and their pullbacks in the per-Gaussian
+ * backward, so no activated copy, concatenated SH array or split/sliced gradient ever touches HBM.
+ *   features_dc (3,1,N); features_rest (3,K-1,N) (NULL when K == 1); scales_raw (3,N), or (1,N) when isotropic != 0;
+ *   vscales_raw has the shape of scales_raw.  Everything else as gsr_forward / gsr_backward. */
+GSR_API int gsr_forward_raw(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K,
+                            const float *means_dev, const float *features_dc_dev, const float *features_rest_dev,
+                            const float *opacities_raw_dev, const float *scales_raw_dev, int32_t isotropic,
+                            const float *rotations_dev, const float background[3], float *image_dev,
+                            uint8_t *covisibilities_dev, float *uncertainties_dev, int64_t *n_rendered, void *stream);
+GSR_API int gsr_backward_raw(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t sh_degree, int32_t K,
+                             const float *means_dev, const float *features_dc_dev, const float *features_rest_dev,
+                             const float *opacities_raw_dev, const float *scales_raw_dev, int32_t isotropic,
+                             const float *rotations_dev, const float background[3], const float *vpixels_dev,
+                             float *vmeans_dev, float *vfeatures_dc_dev, float *vfeatures_rest_dev,
+                             float *vopacities_raw_dev, float *vscales_raw_dev, float *vrot_dev, float *vR_dev,
+                             float *vt_dev, int32_t accumulate, void *stream);
+
 /* ---- the loss either side of the path ------------------------------------------------
  * Fused SSIM.  Arrays are the reference's (W,H,CH,B) column-major Float32, i.e. planar [b][c][y][x]; any W, H
  * (zero padding outside the image, 11-tap sigma=1.5 window).  No handle: stateless, errors via the return code
