@@ -151,6 +151,36 @@ function GSP.update_stats!(strategy::GSP.DefaultStrategy, rast::GaussianRasteriz
         pointer(strategy.denom), stream_ptr()), h)
 end
 
+# ---- fused SSIM — replaces the two kernel launches of fused_ssim.jl:354-389; the rrule (:397-407) is unchanged ----
+function GSP._fused_ssim(img::CuArray{Float32, 4}; ref::CuArray{Float32, 4}, C1::Float32 = 0.01f0^2,
+                         C2::Float32 = 0.03f0^2, train::Bool)
+    W, H, CH, B = size(img)
+    ssim_map = CuArray{Float32}(undef, W, H, CH, B)
+    d = ntuple(_ -> train ? CuArray{Float32}(undef, W, H, CH, B) : CuArray{Float32}(undef, 0, 0, 0, 0), 3)
+    check(ccall((:gsr_ssim_forward, libgsrast), Cint,
+        (Int32, Int32, Int32, Int32, CuPtr{Float32}, CuPtr{Float32}, Float32, Float32, Int32, CuPtr{Float32},
+         CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Ptr{Cvoid}),
+        W, H, CH, B, pointer(img), pointer(ref), C1, C2, train, pointer(ssim_map),
+        train ? pointer(d[1]) : CU_NULL, train ? pointer(d[2]) : CU_NULL, train ? pointer(d[3]) : CU_NULL, stream_ptr()))
+    return ssim_map, d...
+end
+
+function GSP.fused_ssim_bwd(img::T, ref::T, dL_dmap::T, dm_dmu1::T, dm_dsigma1_sq::T, dm_dsigma12::T;
+                            C1::Float32 = 0.01f0^2, C2::Float32 = 0.03f0^2) where T <: CuArray{Float32, 4}
+    W, H, CH, B = size(img)
+    dL_dimg = CuArray{Float32}(undef, W, H, CH, B)      # every element is written: no zero-fill
+    check(ccall((:gsr_ssim_backward, libgsrast), Cint,
+        (Int32, Int32, Int32, Int32, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32},
+         CuPtr{Float32}, CuPtr{Float32}, Ptr{Cvoid}),
+        W, H, CH, B, pointer(img), pointer(ref), pointer(dL_dmap), pointer(dm_dmu1), pointer(dm_dsigma1_sq),
+        pointer(dm_dsigma12), pointer(dL_dimg), stream_ptr()))
+    return dL_dimg
+end
+
+# The activation-fused functor (gsr_forward_raw / gsr_backward_raw) binds the same way as rasterize / ∇rasterize above:
+# one `rrule` on `(rast::GaussianRasterizer)(means_3d, opacities, scales, rotations, sh_color, sh_remainder; ...)` whose
+# forward calls :gsr_forward_raw and whose pullback calls :gsr_backward_raw (argument order in include/gsrast.h).
+
 GSP.release_scene_buffers!(rast::GaussianRasterizer) =
     check(ccall((:gsr_release_scene_buffers, libgsrast), Cint, (Ptr{Cvoid},), handle(rast)))
 
