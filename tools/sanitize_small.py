@@ -22,3 +22,27 @@ for mode, C, deg in (("rgb", 3, 0), ("rgbd", 5, 3), ("rgbdn", 8, 2)):
         torch.cuda.synchronize()
         print(mode, mm, "M", rast.n_rendered, float(g["vmeans"].abs().sum()))
 print("done")
+
+# raw-parameter path, SSIM operator and photometric loss
+from gsrast import ssim
+sc = make_scene(2000, 3, 160, 128, 9)
+cam = Camera(fx=sc.fx, fy=sc.fy, width=160, height=128)
+d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+rast = GaussianRasterizer(width=160, height=128, mode="rgbd")
+raw = dict(means=d(sc.means), opac=d(np.log(sc.opacities / (1 - sc.opacities)).reshape(-1, 1).clip(-12, 12).astype(np.float32)),
+           scales=d(np.log(sc.scales).astype(np.float32)), rots=d(sc.rotations), dc=d(sc.shs[:, :1]), rest=d(sc.shs[:, 1:]))
+for iso in (False, True):
+    scl = raw["scales"][:, :1].contiguous() if iso else raw["scales"]
+    img = rast._raw_call(False, raw["means"], raw["opac"], scl, raw["rots"], raw["dc"], raw["rest"], None, None, cam, 3, (0, 0, 0),
+                         image=rast.image)
+    loss, vpix = ssim.photometric_loss(rast, img, torch.rand((3, 128, 160), device="cuda"), 0.2)
+    g = rast._raw_call(True, raw["means"], raw["opac"], scl, raw["rots"], raw["dc"], raw["rest"], None, None, cam, 3, (0, 0, 0),
+                       vpixels=vpix)
+    torch.cuda.synchronize()
+    print("raw iso", iso, float(loss[0]), float(g["vscales"].abs().sum()))
+x, t = torch.rand((2, 3, 37, 53), device="cuda"), torch.rand((2, 3, 37, 53), device="cuda")
+m, d0, d1, d2 = ssim.ssim_forward(x, t, train=True)
+gg = ssim.ssim_backward(x, t, torch.rand_like(x), d0, d1, d2)
+torch.cuda.synchronize()
+print("ssim", float(m.mean()), float(gg.abs().sum()))
+print("done 2")
