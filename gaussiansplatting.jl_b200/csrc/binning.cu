@@ -288,12 +288,12 @@ struct SortSmem {
     uint32_t tile;
 };
 
-template <int SORT_IPT>
+template <int SORT_IPT, bool BALLOT>
 __global__ void __launch_bounds__(SORT_THREADS)
 onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, const int64_t m, const int shift,
                 const int depth_bits, const uint32_t depth_base, const uint32_t *__restrict__ ghist /* [256] */,
-                uint32_t *status /* [tiles][256] */, uint32_t *tile_counter) {
+                uint32_t *status /* [tiles][256] */, uint32_t *tile_counter, const int ballot_bits) {
     constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmem<SORT_IPT> &S = *reinterpret_cast<SortSmem<SORT_IPT> *>(smem_raw);
@@ -324,7 +324,21 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
         const int local = warp * (32 * SORT_IPT) + j * 32 + lane;
         const bool valid = local < cnt;
         const uint32_t d = valid ? (uint32_t)((compact_key(key[j], depth_bits, depth_base) >> shift) & 255u) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        // lanes holding the same digit.  MATCH.ANY's latency is data dependent: on digits made of tile bits
+        // (runs of neighbouring tiles from one Gaussian) it is ~3x that on depth bits (ncu: 32 % of the pass's
+        // stall samples sit on its consumer), so those passes build the mask from one ballot per digit bit instead
+        unsigned peers;
+        if (!BALLOT) {
+            peers = __match_any_sync(0xffffffffu, d);
+        } else {
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            peers = valid ? vmask : ~vmask;
+            for (int b = 0; b < ballot_bits; b++) {
+                const bool bit = (d >> b) & 1u;
+                const unsigned bal = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? bal : ~bal;
+            }
+        }
         const int leader = __ffs(peers) - 1;
         uint32_t pre = 0;
         if (valid && lane == leader) {
@@ -511,8 +525,10 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
     if (m <= 0) return;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(onesweep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<8>));
-        cudaFuncSetAttribute(onesweep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<16>));
+        cudaFuncSetAttribute(onesweep_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<8>));
+        cudaFuncSetAttribute(onesweep_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<16>));
+        cudaFuncSetAttribute(onesweep_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<8>));
+        cudaFuncSetAttribute(onesweep_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<16>));
         attr_set = true;
     }
     const int ipt = sort_ipt();
@@ -528,19 +544,30 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
     }
     const uint64_t *ksrc = keys_in;
     const uint32_t *vsrc = vals_in;
+    static int rank_mode = -1;  // GSR_SORT_RANK = match | ballot | auto (default)
+    if (rank_mode < 0) {
+        const char *e = getenv("GSR_SORT_RANK");
+        rank_mode = (e && !strcmp(e, "match")) ? 0 : ((e && !strcmp(e, "ballot")) ? 1 : 2);
+    }
+    const int total_bits = plan.tile_bits + plan.depth_bits;
     for (int p = 0; p < plan.passes; p++) {
+        const int digit_bits = total_bits - 8 * p < 8 ? total_bits - 8 * p : 8;
+        const bool has_tile_bits = 8 * p + 8 > plan.depth_bits;
+        const int ballot_bits = (rank_mode == 1 || (rank_mode == 2 && has_tile_bits)) ? digit_bits : 0;
         // the chain must end in (keys_out, vals_out) and never write the input
         const bool to_out = ((plan.passes - 1 - p) % 2) == 0;
         uint64_t *kdst = to_out ? keys_out : keys_tmp;
         uint32_t *vdst = to_out ? vals_out : vals_tmp;
-        if (ipt == 16)
-            onesweep_kernel<16><<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem<16>), s>>>(
-                ksrc, vsrc, kdst, vdst, m, 8 * p, plan.depth_bits, plan.depth_base, ghist + (size_t)p * 256,
-                status + (size_t)p * tiles * 256, counters + p);
-        else
-            onesweep_kernel<8><<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem<8>), s>>>(
-                ksrc, vsrc, kdst, vdst, m, 8 * p, plan.depth_bits, plan.depth_base, ghist + (size_t)p * 256,
-                status + (size_t)p * tiles * 256, counters + p);
+#define GSR_ONESWEEP(IPT, BAL)                                                                                       \
+    onesweep_kernel<IPT, BAL><<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem<IPT>), s>>>(                              \
+        ksrc, vsrc, kdst, vdst, m, 8 * p, plan.depth_bits, plan.depth_base, ghist + (size_t)p * 256,                    \
+        status + (size_t)p * tiles * 256, counters + p, ballot_bits)
+        if (ipt == 16) {
+            if (ballot_bits) GSR_ONESWEEP(16, true); else GSR_ONESWEEP(16, false);
+        } else {
+            if (ballot_bits) GSR_ONESWEEP(8, true); else GSR_ONESWEEP(8, false);
+        }
+#undef GSR_ONESWEEP
         count_launch();
         ksrc = kdst;
         vsrc = vdst;
