@@ -64,7 +64,7 @@ __device__ __forceinline__ void put(float *p, float v) {
     if (ACC) *p += v; else *p = v;
 }
 
-template <bool ACC>
+template <bool ACC, bool RAW>
 __global__ void __launch_bounds__(BG_THREADS, 5)
 backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_degree, const int K, const int channels,
                           const float *__restrict__ means, const float *__restrict__ shs,
@@ -91,7 +91,7 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
     const bool aligned16 = (((uintptr_t)shs | (uintptr_t)vshs) & 15) == 0;
     if (__syncthreads_or(visible_t) && sh_degree > 0) {
         if (k_used == K) {
-            if (ps.sh_rest) {
+            if (RAW && ps.sh_rest) {
                 rows_global_to_shared(shs + block0 * 3, s_sh, (int)nb, 3, sh_stride, tid, BG_THREADS, false);
                 if (K > 1)
                     rows_global_to_shared(ps.sh_rest + block0 * (int64_t)(row - 3), s_sh + 3, (int)nb, row - 3, sh_stride, tid,
@@ -100,7 +100,7 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
                 rows_global_to_shared(shs + block0 * row, s_sh, (int)nb, row, sh_stride, tid, BG_THREADS, aligned16);
             }
         } else if (visible_t) {
-            if (ps.sh_rest) {
+            if (RAW && ps.sh_rest) {
                 for (int e = 0; e < 3; e++) s_sh[tid * sh_stride + e] = shs[3 * i + e];
                 const float *src = ps.sh_rest + i * (int64_t)(row - 3);
                 for (int e = 3; e < 3 * k_used; e++) s_sh[tid * sh_stride + e] = src[e - 3];
@@ -123,7 +123,7 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
             if (!ACC) {
 #pragma unroll
                 for (int k = 0; k < 3; k++) vmeans[3 * i + k] = 0.f;
-                if (ps.isotropic) vscales[i] = 0.f;
+                if (RAW && ps.isotropic) vscales[i] = 0.f;
                 else
 #pragma unroll
                     for (int k = 0; k < 3; k++) vscales[3 * i + k] = 0.f;
@@ -143,9 +143,9 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
             const float ca = g.conics[3 * i], cb = g.conics[3 * i + 1], cc = g.conics[3 * i + 2];
             const float vm2[2] = {ca * a0.x + cb * a0.y, cb * a0.x + cc * a0.y};
             const float vcn[3] = {0.5f * a0.z, 0.5f * a0.w, 0.5f * a1.x};
-            const float op = ps.raw_opacity ? act_sigmoid(opac[i]) : opac[i];
+            const float op = (RAW && ps.raw_opacity) ? act_sigmoid(opac[i]) : opac[i];
             float vop = op > 0.0f ? a1.y / op : 0.0f;
-            if (ps.raw_opacity) vop *= op * (1.0f - op);  // pullback of sigmoid (rasterizer.jl:229)
+            if (RAW && ps.raw_opacity) vop *= op * (1.0f - op);  // pullback of sigmoid (rasterizer.jl:229)
             float vcol[8] = {a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, 0.f, 0.f};
             if (channels > 5) {
                 const float4 a3 = *reinterpret_cast<const float4 *>(acc + 12);
@@ -168,11 +168,11 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
             }
             const float mean[3] = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
             float sc[3];
-            if (ps.isotropic) {
+            if (RAW && ps.isotropic) {
                 sc[0] = sc[1] = sc[2] = expf(scales[i]);
             } else {
                 sc[0] = scales[3 * i]; sc[1] = scales[3 * i + 1]; sc[2] = scales[3 * i + 2];
-                if (ps.raw_scale) { sc[0] = expf(sc[0]); sc[1] = expf(sc[1]); sc[2] = expf(sc[2]); }
+                if (RAW && ps.raw_scale) { sc[0] = expf(sc[0]); sc[1] = expf(sc[1]); sc[2] = expf(sc[2]); }
             }
             const float4 q4 = *reinterpret_cast<const float4 *>(rots + 4 * i);
 
@@ -416,11 +416,11 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
 
 #pragma unroll
             for (int k = 0; k < 3; k++) put<ACC>(vmeans + 3 * i + k, vmean[k]);
-            if (ps.raw_scale || ps.isotropic) {  // pullback of exp: d exp(s) = exp(s) ds (rasterizer.jl:237)
+            if (RAW && (ps.raw_scale || ps.isotropic)) {  // pullback of exp: d exp(s) = exp(s) ds (rasterizer.jl:237)
 #pragma unroll
                 for (int k = 0; k < 3; k++) vscale[k] *= sc[k];
             }
-            if (ps.isotropic) {
+            if (RAW && ps.isotropic) {
                 put<ACC>(vscales + i, (vscale[0] + vscale[1]) + vscale[2]);  // pullback of vcat(s, s, s)
             } else {
 #pragma unroll
@@ -439,7 +439,7 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
     // coalesced write-out of the CTA's SH-gradient span
     __syncthreads();
     {
-        if (ps.sh_rest) {
+        if (RAW && ps.sh_rest) {
             rows_shared_to_global<ACC>(vshs + block0 * 3, s_sh, (int)nb, 3, sh_stride, tid, BG_THREADS, false);
             if (K > 1)
                 rows_shared_to_global<ACC>(ps.vsh_rest + block0 * (int64_t)(row - 3), s_sh + 3, (int)nb, row - 3, sh_stride, tid,
@@ -538,14 +538,17 @@ void launch_backward_gaussians(const DevCamera &cam, int64_t n, int sh_degree, i
     int stride = 3 * K;
     if ((stride & 1) == 0) stride += 1;
     const size_t smem = (size_t)BG_THREADS * stride * sizeof(float);
-    if (accumulate)
-        backward_gaussians_kernel<true><<<blocks, BG_THREADS, smem, s>>>(cam, n, sh_degree, K, channels, means, shs, opac,
-                                                                        scales, rots, g, vmeans, vshs, vopac, vscales,
-                                                                        vrot, vR, vt, stride, ps);
-    else
-        backward_gaussians_kernel<false><<<blocks, BG_THREADS, smem, s>>>(cam, n, sh_degree, K, channels, means, shs, opac,
-                                                                         scales, rots, g, vmeans, vshs, vopac, vscales,
-                                                                         vrot, vR, vt, stride, ps);
+    const bool raw = ps.raw_opacity || ps.raw_scale || ps.isotropic || ps.sh_rest;
+#define GSR_BG(AC, RW)                                                                                                    \
+    backward_gaussians_kernel<AC, RW><<<blocks, BG_THREADS, smem, s>>>(cam, n, sh_degree, K, channels, means, shs, opac,    \
+                                                                     scales, rots, g, vmeans, vshs, vopac, vscales, vrot, \
+                                                                     vR, vt, stride, ps)
+    if (accumulate) {
+        if (raw) GSR_BG(true, true); else GSR_BG(true, false);
+    } else {
+        if (raw) GSR_BG(false, true); else GSR_BG(false, false);
+    }
+#undef GSR_BG
     count_launch();
 }
 

@@ -54,7 +54,7 @@ __device__ __forceinline__ void transpose33(const float *A, float *T) {
 #define SH3C7 -0.5900435899266435f
 #define EPS32 1.1920929e-07f
 
-template <bool ALIGNED16>
+template <bool ALIGNED16, bool RAW>
 __global__ void __launch_bounds__(PP_THREADS, 8)
 preprocess_kernel(const DevCamera cam, const int64_t n, const int sh_degree, const int K, const int channels,
                   const float *__restrict__ means, const float *__restrict__ shs, const float *__restrict__ opac,
@@ -90,11 +90,11 @@ preprocess_kernel(const DevCamera cam, const int64_t n, const int sh_degree, con
         if (cam.near_plane < mc[2] && mc[2] < cam.far_plane) {  // projection.jl:79
             const float4 q4 = *reinterpret_cast<const float4 *>(rots + 4 * i);  // 128-bit load (simd.jl:1-11)
             float sc[3];
-            if (ps.isotropic) {
+            if (RAW && ps.isotropic) {
                 sc[0] = sc[1] = sc[2] = expf(scales[i]);  // rasterizer.jl:240-243
             } else {
                 sc[0] = scales[3 * i]; sc[1] = scales[3 * i + 1]; sc[2] = scales[3 * i + 2];
-                if (ps.raw_scale) { sc[0] = expf(sc[0]); sc[1] = expf(sc[1]); sc[2] = expf(sc[2]); }
+                if (RAW && ps.raw_scale) { sc[0] = expf(sc[0]); sc[1] = expf(sc[1]); sc[2] = expf(sc[2]); }
             }
             // unnorm_quat2rot (render.jl:322-333): normalize(q) = inv(norm(q)) * q
             const float qn = sqrtf(((q4.x * q4.x + q4.y * q4.y) + q4.z * q4.z) + q4.w * q4.w);
@@ -186,7 +186,7 @@ preprocess_kernel(const DevCamera cam, const int64_t n, const int sh_degree, con
     if (any_visible) {
         if (k_used == K) {
             const int nb = (int)((n - block0) < PP_THREADS ? (n - block0) : PP_THREADS);
-            if (ps.sh_rest) {  // features_dc | features_rest kept apart by the caller: same rows, two spans
+            if (RAW && ps.sh_rest) {  // features_dc | features_rest kept apart by the caller: same rows, two spans
                 rows_global_to_shared(shs + block0 * 3, s_sh, nb, 3, sh_stride, tid, PP_THREADS, false);
                 if (K > 1)
                     rows_global_to_shared(ps.sh_rest + block0 * (int64_t)(3 * (K - 1)), s_sh + 3, nb, 3 * (K - 1), sh_stride, tid,
@@ -195,7 +195,7 @@ preprocess_kernel(const DevCamera cam, const int64_t n, const int sh_degree, con
                 rows_global_to_shared(shs + block0 * (int64_t)(3 * K), s_sh, nb, 3 * K, sh_stride, tid, PP_THREADS, ALIGNED16);
             }
         } else if (visible) {  // k_used < K: only the leading coefficients are needed — direct strided loads
-            if (ps.sh_rest) {
+            if (RAW && ps.sh_rest) {
                 for (int e = 0; e < 3; e++) s_sh[tid * sh_stride + e] = shs[3 * i + e];
                 const float *src = ps.sh_rest + i * (int64_t)(3 * (K - 1));
                 for (int e = 3; e < 3 * k_used; e++) s_sh[tid * sh_stride + e] = src[e - 3];
@@ -268,7 +268,7 @@ preprocess_kernel(const DevCamera cam, const int64_t n, const int sh_degree, con
     if (channels > 5) { g.normals[3 * i] = nrm[0]; g.normals[3 * i + 1] = nrm[1]; g.normals[3 * i + 2] = nrm[2]; }
 
     // packed record for the compositing kernels; features = rgb, depth, 1, normal (rasterizer.jl:380-386)
-    const float o = ps.raw_opacity ? act_sigmoid(opac[i]) : opac[i];
+    const float o = (RAW && ps.raw_opacity) ? act_sigmoid(opac[i]) : opac[i];
     const int RQ = rec_quads(channels);
     float4 *rec = g.rec + i * RQ;
     rec[0] = make_float4(m2[0], m2[1], conic[0], conic[1]);
@@ -292,11 +292,15 @@ void launch_preprocess(const DevCamera &cam, int64_t n, int sh_degree, int K, in
     const size_t smem = (size_t)PP_THREADS * stride * sizeof(float);
     const int64_t blocks = (n + PP_THREADS - 1) / PP_THREADS;
     const bool aligned = (reinterpret_cast<uintptr_t>(shs) & 15) == 0;
-    if (aligned)
-        preprocess_kernel<true><<<(unsigned)blocks, PP_THREADS, smem, s>>>(cam, n, sh_degree, K, channels, means, shs,
-                                                                          opac, scales, rots, g, stride, ps);
-    else
-        preprocess_kernel<false><<<(unsigned)blocks, PP_THREADS, smem, s>>>(cam, n, sh_degree, K, channels, means,
-                                                                           shs, opac, scales, rots, g, stride, ps);
+    const bool raw = ps.raw_opacity || ps.raw_scale || ps.isotropic || ps.sh_rest;
+#define GSR_PP(AL, RW)                                                                                                   \
+    preprocess_kernel<AL, RW><<<(unsigned)blocks, PP_THREADS, smem, s>>>(cam, n, sh_degree, K, channels, means, shs, opac, \
+                                                                       scales, rots, g, stride, ps)
+    if (aligned) {
+        if (raw) GSR_PP(true, true); else GSR_PP(true, false);
+    } else {
+        if (raw) GSR_PP(false, true); else GSR_PP(false, false);
+    }
+#undef GSR_PP
     count_launch();
 }
