@@ -40,7 +40,8 @@ EXPORTS = ["gsr_version", "gsr_last_error", "gsr_create", "gsr_destroy", "gsr_re
            "gsr_forward_backward_host", "gsr_identify_tile_range", "gsr_sort_pairs", "gsr_launch_count",
            "gsr_profile_enable", "gsr_profile_get", "gsr_measure_fp32_peak", "gsr_forward_backward_host_async",
            "gsr_host_wait", "gsr_host_timeline", "gsr_set_accumulator", "gsr_backward_render",
-           "gsr_backward_gaussians_peers", "gsr_ssim_forward", "gsr_ssim_backward", "gsr_photometric_loss", "gsr_forward_raw", "gsr_backward_raw"]
+           "gsr_backward_gaussians_peers", "gsr_ssim_forward", "gsr_ssim_backward", "gsr_photometric_loss", "gsr_forward_raw", "gsr_backward_raw", "gsr_ply_open", "gsr_ply_read",
+           "gsr_ply_close", "gsr_ply_write", "gsr_ply_last_error"]
 STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "render_fwd", "zero_grads", "render_bwd", "gauss_bwd"]
 
 
@@ -91,6 +92,12 @@ def load() -> C.CDLL:
     lib.gsr_ssim_forward.argtypes = [i32, i32, i32, i32, vp, vp, C.c_float, C.c_float, i32, vp, vp, vp, vp, vp]
     lib.gsr_ssim_backward.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.gsr_photometric_loss.argtypes = [vp, vp, vp, C.c_float, vp, vp, vp]
+    lib.gsr_ply_open.argtypes = [C.c_char_p, C.POINTER(i64), C.POINTER(i32), C.POINTER(vp)]
+    lib.gsr_ply_read.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.gsr_ply_close.argtypes = [vp]
+    lib.gsr_ply_close.restype = None
+    lib.gsr_ply_write.argtypes = [C.c_char_p, i64, i32, vp, vp, vp, vp, vp, vp]
+    lib.gsr_ply_last_error.restype = C.c_char_p
     lib.gsr_identify_tile_range.argtypes = [vp, i64, vp, vp]
     lib.gsr_sort_pairs.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     lib.gsr_launch_count.restype = i64

@@ -236,6 +236,21 @@ GSR_API int gsr_ssim_backward(int32_t width, int32_t height, int32_t channels, i
 GSR_API int gsr_photometric_loss(GsrHandle *h, const float *image_dev, const float *target_dev, float lambda_dssim,
                                  float *vpixels_dev, float *loss_dev, void *stream);
 
+/* ---- getting real scenes in and out (host side, no GPU involved) ------------------------
+ * 3DGS `.ply` files as read / written by import_ply / export_ply (gaussians.jl:157-247, via PlyIO.jl there).
+ * Properties are matched by NAME (order and storage type free; ascii, little- and big-endian binary); f_rest_* is
+ * channel-major in the file and (3,R,N) in memory.  Arrays are HOST buffers in the reference's model layout and hold
+ * the RAW parameters gsr_forward_raw takes: points (3,N), features_dc (3,1,N), features_rest (3,R,N), opacities (1,N)
+ * pre-sigmoid, scales (3,N) log, rotations (4,N) wxyz.  Errors: GSR_EINVAL + gsr_ply_last_error(). */
+GSR_API int gsr_ply_open(const char *path, int64_t *n, int32_t *n_rest_coeffs /* R = K-1 per channel */, void **reader);
+GSR_API int gsr_ply_read(void *reader, float *points, float *features_dc, float *features_rest, float *opacities,
+                         float *scales, float *rotations);
+GSR_API void gsr_ply_close(void *reader);
+GSR_API int gsr_ply_write(const char *path, int64_t n, int32_t n_rest_coeffs, const float *points,
+                          const float *features_dc, const float *features_rest, const float *opacities,
+                          const float *scales, const float *rotations);
+GSR_API const char *gsr_ply_last_error(void);
+
 /* Per-stage device timing (CUDA events on the caller's stream; SURVEY.md §5 "tracing / profiling").
  * When enabled, gsr_forward / gsr_backward bracket each stage with events; gsr_profile_get synchronises on
  * them and returns the durations of the last forward + backward in milliseconds (0 for stages that did not run). */
