@@ -65,7 +65,7 @@ __device__ __forceinline__ void put(float *p, float v) {
 }
 
 template <bool ACC, bool RAW>
-__global__ void __launch_bounds__(BG_THREADS, 5)
+__global__ void __launch_bounds__(BG_THREADS, 6)
 backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_degree, const int K, const int channels,
                           const float *__restrict__ means, const float *__restrict__ shs,
                           const float *__restrict__ opac, const float *__restrict__ scales, const float *__restrict__ rots, const GeomPtrs g,

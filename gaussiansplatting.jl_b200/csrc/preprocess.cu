@@ -55,7 +55,7 @@ __device__ __forceinline__ void transpose33(const float *A, float *T) {
 #define EPS32 1.1920929e-07f
 
 template <bool ALIGNED16, bool RAW>
-__global__ void __launch_bounds__(PP_THREADS, 8)
+__global__ void __launch_bounds__(PP_THREADS, 6)
 preprocess_kernel(const DevCamera cam, const int64_t n, const int sh_degree, const int K, const int channels,
                   const float *__restrict__ means, const float *__restrict__ shs, const float *__restrict__ opac,
                   const float *__restrict__ scales, const float *__restrict__ rots, const GeomPtrs g,
