@@ -429,21 +429,35 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
 // ----------------------------------------------------------------------------------------------------------
 // identify_tile_range! — utils.jl:56-78   (ranges pre-zeroed by the caller, rasterizer.jl:375)
 // ----------------------------------------------------------------------------------------------------------
+constexpr int RANGES_IPT = 4;  // keys per thread: two 128-bit loads instead of 2 x 4 scalar ones
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(const int64_t m, const uint64_t *__restrict__ keys, uint32_t *__restrict__ ranges) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const uint32_t tile = (uint32_t)(keys[i] >> 32);
-    if (i == 0) {
-        ranges[2 * (int64_t)tile] = 0u;
+tile_ranges_kernel(const int64_t m, const uint64_t *__restrict__ keys, uint32_t *__restrict__ ranges, const bool aligned16) {
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * RANGES_IPT;
+    if (i0 >= m) return;
+    uint64_t k[RANGES_IPT];
+    if (aligned16 && i0 + RANGES_IPT <= m) {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(keys + i0);
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(keys + i0 + 2);
+        k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y;
     } else {
-        const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
-        if (tile != prev) {
+#pragma unroll
+        for (int j = 0; j < RANGES_IPT; j++) k[j] = i0 + j < m ? keys[i0 + j] : 0ull;
+    }
+    uint32_t prev = i0 > 0 ? (uint32_t)(keys[i0 - 1] >> 32) : 0u;
+#pragma unroll
+    for (int j = 0; j < RANGES_IPT; j++) {
+        const int64_t i = i0 + j;
+        if (i >= m) break;
+        const uint32_t tile = (uint32_t)(k[j] >> 32);
+        if (i == 0) {
+            ranges[2 * (int64_t)tile] = 0u;
+        } else if (tile != prev) {
             ranges[2 * (int64_t)prev + 1] = (uint32_t)i;
             ranges[2 * (int64_t)tile] = (uint32_t)i;
         }
+        if (i == m - 1) ranges[2 * (int64_t)tile + 1] = (uint32_t)m;
+        prev = tile;
     }
-    if (i == m - 1) ranges[2 * (int64_t)tile + 1] = (uint32_t)m;
 }
 
 int bit_length(uint64_t x) {
@@ -576,6 +590,8 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
 
 void launch_tile_ranges(int64_t m, const uint64_t *keys_sorted, uint32_t *ranges, cudaStream_t s) {
     if (m <= 0) return;
-    tile_ranges_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(m, keys_sorted, ranges);
+    const int64_t per_block = 256 * RANGES_IPT;
+    tile_ranges_kernel<<<(unsigned)((m + per_block - 1) / per_block), 256, 0, s>>>(m, keys_sorted, ranges,
+                                                                                    (reinterpret_cast<uintptr_t>(keys_sorted) & 15) == 0);
     count_launch();
 }
