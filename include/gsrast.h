@@ -8,6 +8,9 @@
  * plus the state other components read (rast.gstate.radii, rast.gstate.∇means_2d — src/strategy.jl:85-86)
  * and `_update_stats!` (src/strategy.jl:118-136).  ext/GaussianSplattingCUDAExt would `ccall` the entry
  * points below in place of the KernelAbstractions kernel launches (INTEGRATION.md shows the binding).
+ * Widened per SURVEY.md §8(f): the activation-fused functor (gsr_forward_raw / gsr_backward_raw), the fused SSIM
+ * operator and photometric loss (gsr_ssim_*, gsr_photometric_loss), 3DGS .ply files (gsr_ply_*), and the multi-GPU
+ * split of the backward (gsr_set_accumulator / gsr_backward_render / gsr_backward_gaussians_peers).
  *
  * Conventions
  *   - every pointer named *_dev / documented "device" is a CUDA device pointer owned by the caller;
