@@ -130,6 +130,20 @@ int launch_backward_gaussians_peers(const PeerArgs &args, cudaStream_t s);
 
 void count_launch(int n = 1);
 
+// ---- densification kernels (densify.cu) ----------------------------------------------------------------------
+int launch_densify_masks(int64_t n, int64_t n_grad, const float *accum, const float *denom, const float *scales,
+                         int isotropic, float grad_threshold, float gamma, uint8_t *clone_mask, uint8_t *split_mask,
+                         cudaStream_t s);
+int launch_prune_mask(int64_t n, const float *opacities, const float *scales, int isotropic, const int32_t *max_radii,
+                      float min_opacity, int32_t max_screen_size, float gamma, uint8_t *valid, cudaStream_t s);
+size_t mask_offsets_scratch_words(int64_t n);
+int launch_mask_offsets(int64_t n, const uint8_t *mask, int32_t *offsets, int64_t *count_dev, int32_t *scratch,
+                        cudaStream_t s);
+int launch_gather_rows(int64_t n, int row_words, const void *src, const uint8_t *mask, const int32_t *offsets, void *dst,
+                       int repeat, int64_t count, cudaStream_t s);
+int launch_split_children(int64_t m, float *points, float *scales, int isotropic, const float *rotations,
+                          const float *noise, int n_split, cudaStream_t s);
+
 // ---- fused SSIM / photometric loss (ssim.cu) -----------------------------------------------------------------
 int launch_ssim_forward(int W, int H, int CH, int B, const float *img, const float *ref, float C1, float C2, int train,
                         float *ssim_map, float *dm_dmu1, float *dm_dsigma1_sq, float *dm_dsigma12, cudaStream_t s);

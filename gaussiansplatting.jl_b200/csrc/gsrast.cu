@@ -783,6 +783,69 @@ int gsr_measure_fp32_peak(double *tflops, void *stream) {
     return GSR_OK;
 }
 
+int gsr_densify_masks(int64_t n, int64_t n_grad, const float *accum_dev, const float *denom_dev, const float *scales_dev,
+                      int32_t isotropic, float grad_threshold, float gamma, uint8_t *clone_mask_dev,
+                      uint8_t *split_mask_dev, void *stream) {
+    GsrHandle *h = nullptr;
+    if (n < 0 || n_grad < 0 || n_grad > n) return fail(h, GSR_EINVAL, "gsr_densify_masks: need 0 <= n_grad <= n");
+    if (n > 0 && (!scales_dev || (n_grad > 0 && (!accum_dev || !denom_dev)))) return fail(h, GSR_EINVAL, "gsr_densify_masks: null argument");
+    if (launch_densify_masks(n, n_grad, accum_dev, denom_dev, scales_dev, isotropic, grad_threshold, gamma, clone_mask_dev,
+                             split_mask_dev, static_cast<cudaStream_t>(stream)))
+        return cuda_fail(h, cudaGetLastError(), "densify_masks_kernel");
+    return GSR_OK;
+}
+
+int gsr_prune_mask(int64_t n, const float *opacities_dev, const float *scales_dev, int32_t isotropic,
+                   const int32_t *max_radii_dev, float min_opacity, int32_t max_screen_size, float gamma,
+                   uint8_t *valid_mask_dev, void *stream) {
+    GsrHandle *h = nullptr;
+    if (n < 0) return fail(h, GSR_EINVAL, "gsr_prune_mask: n < 0");
+    if (n > 0 && (!opacities_dev || !valid_mask_dev || (max_screen_size > 0 && (!max_radii_dev || !scales_dev))))
+        return fail(h, GSR_EINVAL, "gsr_prune_mask: null argument");
+    if (launch_prune_mask(n, opacities_dev, scales_dev, isotropic, max_radii_dev, min_opacity, max_screen_size, gamma,
+                          valid_mask_dev, static_cast<cudaStream_t>(stream)))
+        return cuda_fail(h, cudaGetLastError(), "prune_mask_kernel");
+    return GSR_OK;
+}
+
+size_t gsr_mask_offsets_scratch_words(int64_t n) { return n > 0 ? mask_offsets_scratch_words(n) : 1; }
+
+int gsr_mask_offsets(int64_t n, const uint8_t *mask_dev, int32_t *offsets_dev, int64_t *count_dev, int32_t *scratch_dev,
+                     void *stream) {
+    GsrHandle *h = nullptr;
+    if (n < 0 || n >= (1ll << 31) || !count_dev) return fail(h, GSR_EINVAL, "gsr_mask_offsets: bad argument");
+    if (n > 0 && (!mask_dev || !offsets_dev || !scratch_dev)) return fail(h, GSR_EINVAL, "gsr_mask_offsets: null argument");
+    if (launch_mask_offsets(n, mask_dev, offsets_dev, count_dev, scratch_dev, static_cast<cudaStream_t>(stream)))
+        return cuda_fail(h, cudaGetLastError(), "mask_offsets");
+    return GSR_OK;
+}
+
+int gsr_gather_rows(int64_t n, int32_t row_bytes, const void *src_dev, const uint8_t *mask_dev, const int32_t *offsets_dev,
+                    void *dst_dev, int32_t repeat, int64_t count, void *stream) {
+    GsrHandle *h = nullptr;
+    if (n < 0 || row_bytes < 0 || (row_bytes & 3) || repeat < 1 || count < 0)
+        return fail(h, GSR_EINVAL, "gsr_gather_rows: need row_bytes % 4 == 0, repeat >= 1");
+    if (n == 0 || row_bytes == 0 || count == 0) return GSR_OK;
+    if (!src_dev || !mask_dev || !offsets_dev || !dst_dev) return fail(h, GSR_EINVAL, "gsr_gather_rows: null argument");
+    if (launch_gather_rows(n, row_bytes / 4, src_dev, mask_dev, offsets_dev, dst_dev, repeat, count,
+                           static_cast<cudaStream_t>(stream)))
+        return cuda_fail(h, cudaGetLastError(), "gather_rows_kernel");
+    return GSR_OK;
+}
+
+int gsr_split_children(int64_t m, float *points_dev, float *scales_dev, int32_t isotropic, const float *rotations_dev,
+                       const float *noise_dev, int32_t n_split, void *stream) {
+    GsrHandle *h = nullptr;
+    if (m < 0 || n_split < 1) return fail(h, GSR_EINVAL, "gsr_split_children: bad argument");
+    if (m == 0) return GSR_OK;
+    if (!points_dev || !scales_dev || !rotations_dev || !noise_dev || (reinterpret_cast<uintptr_t>(rotations_dev) & 15))
+        return fail(h, GSR_EINVAL, "gsr_split_children: null argument or rotations not 16-byte aligned");
+    if (launch_split_children(m, points_dev, scales_dev, isotropic, rotations_dev, noise_dev, n_split,
+                              static_cast<cudaStream_t>(stream)))
+        return cuda_fail(h, cudaGetLastError(), "split_children_kernel");
+    return GSR_OK;
+}
+
 int gsr_ssim_forward(int32_t width, int32_t height, int32_t channels, int32_t batch, const float *img_dev,
                      const float *ref_dev, float C1, float C2, int32_t train, float *ssim_map_dev, float *dm_dmu1_dev,
                      float *dm_dsigma1_sq_dev, float *dm_dsigma12_dev, void *stream) {

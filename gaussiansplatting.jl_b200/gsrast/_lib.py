@@ -41,7 +41,8 @@ EXPORTS = ["gsr_version", "gsr_last_error", "gsr_create", "gsr_destroy", "gsr_re
            "gsr_profile_enable", "gsr_profile_get", "gsr_measure_fp32_peak", "gsr_forward_backward_host_async",
            "gsr_host_wait", "gsr_host_timeline", "gsr_set_accumulator", "gsr_backward_render",
            "gsr_backward_gaussians_peers", "gsr_ssim_forward", "gsr_ssim_backward", "gsr_photometric_loss", "gsr_forward_raw", "gsr_backward_raw", "gsr_ply_open", "gsr_ply_read",
-           "gsr_ply_close", "gsr_ply_write", "gsr_ply_last_error"]
+           "gsr_ply_close", "gsr_ply_write", "gsr_ply_last_error", "gsr_densify_masks", "gsr_prune_mask",
+           "gsr_mask_offsets_scratch_words", "gsr_mask_offsets", "gsr_gather_rows", "gsr_split_children"]
 STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "render_fwd", "zero_grads", "render_bwd", "gauss_bwd"]
 
 
@@ -98,6 +99,13 @@ def load() -> C.CDLL:
     lib.gsr_ply_close.restype = None
     lib.gsr_ply_write.argtypes = [C.c_char_p, i64, i32, vp, vp, vp, vp, vp, vp]
     lib.gsr_ply_last_error.restype = C.c_char_p
+    lib.gsr_densify_masks.argtypes = [i64, i64, vp, vp, vp, i32, C.c_float, C.c_float, vp, vp, vp]
+    lib.gsr_prune_mask.argtypes = [i64, vp, vp, i32, vp, C.c_float, i32, C.c_float, vp, vp]
+    lib.gsr_mask_offsets_scratch_words.argtypes = [i64]
+    lib.gsr_mask_offsets_scratch_words.restype = C.c_size_t
+    lib.gsr_mask_offsets.argtypes = [i64, vp, vp, vp, vp, vp]
+    lib.gsr_gather_rows.argtypes = [i64, i32, vp, vp, vp, vp, i32, i64, vp]
+    lib.gsr_split_children.argtypes = [i64, vp, vp, i32, vp, vp, i32, vp]
     lib.gsr_identify_tile_range.argtypes = [vp, i64, vp, vp]
     lib.gsr_sort_pairs.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     lib.gsr_launch_count.restype = i64

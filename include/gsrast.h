@@ -9,7 +9,8 @@
  * and `_update_stats!` (src/strategy.jl:118-136).  ext/GaussianSplattingCUDAExt would `ccall` the entry
  * points below in place of the KernelAbstractions kernel launches (INTEGRATION.md shows the binding).
  * Widened per SURVEY.md §8(f): the activation-fused functor (gsr_forward_raw / gsr_backward_raw), the fused SSIM
- * operator and photometric loss (gsr_ssim_*, gsr_photometric_loss), 3DGS .ply files (gsr_ply_*), and the multi-GPU
+ * operator and photometric loss (gsr_ssim_*, gsr_photometric_loss), the densification kernels (gsr_densify_masks ...
+ * gsr_split_children), 3DGS .ply files (gsr_ply_*), and the multi-GPU
  * split of the backward (gsr_set_accumulator / gsr_backward_render / gsr_backward_gaussians_peers).
  *
  * Conventions
@@ -214,6 +215,39 @@ GSR_API int gsr_backward_raw(GsrHandle *h, const GsrCamera *cam, int64_t n, int3
                              float *vmeans_dev, float *vfeatures_dc_dev, float *vfeatures_rest_dev,
                              float *vopacities_raw_dev, float *vscales_raw_dev, float *vrot_dev, float *vR_dev,
                              float *vt_dev, int32_t accumulate, void *stream);
+
+/* ---- the densification consumer of radii / ∇means_2d -----------------------------------
+ * The device steps of `densify_and_prune!` (src/densification.jl) as stateless launches over plain device arrays; the
+ * host sequence (clone, split, prune; Adam moments and statistics follow their parameters) is the caller's, as in the
+ * reference (gsrast/densify.py mirrors it).  Arrays are the raw model arrays: scales (3,N) log-scales or (1,N) when
+ * isotropic != 0, opacities pre-sigmoid.  Masks are N bytes (Bool).  Errors via gsr_last_error(NULL). */
+/* ∇ = accum ./ denom with NaN -> 0 for the first n_grad Gaussians (0 for the rest: `padded_grad`, :74-75);
+ * clone_mask = ∇ > threshold && max(exp(scales)) < gamma (:35-38); split_mask = ∇ >= threshold && max(exp(scales)) > gamma
+ * (:78-81); gamma = extent * dense_percent.  Either mask may be NULL. */
+GSR_API int gsr_densify_masks(int64_t n, int64_t n_grad, const float *accum_dev, const float *denom_dev,
+                              const float *scales_dev, int32_t isotropic, float grad_threshold, float gamma,
+                              uint8_t *clone_mask_dev, uint8_t *split_mask_dev, void *stream);
+/* valid = sigmoid(opacity) > min_opacity [&& max_radii < max_screen_size && max(exp(scales)) < gamma when
+ * max_screen_size > 0; gamma = 0.1 * pruning_extent] (:19-25). */
+GSR_API int gsr_prune_mask(int64_t n, const float *opacities_dev, const float *scales_dev, int32_t isotropic,
+                           const int32_t *max_radii_dev, float min_opacity, int32_t max_screen_size, float gamma,
+                           uint8_t *valid_mask_dev, void *stream);
+/* Exclusive prefix of a byte mask (the compaction index every array of the model shares) and the number of set
+ * entries (*count_dev, int64 on the device).  scratch_dev: gsr_mask_offsets_scratch_words(n) int32 words. */
+GSR_API size_t gsr_mask_offsets_scratch_words(int64_t n);
+GSR_API int gsr_mask_offsets(int64_t n, const uint8_t *mask_dev, int32_t *offsets_dev, int64_t *count_dev,
+                             int32_t *scratch_dev, void *stream);
+/* dst[:, j + c*count] = src[:, i] for every i with mask[i], j = offsets[i], c < repeat: the reference's `x[:, mask]`,
+ * `x[:, :, mask]` (prune_points!, densify_clone!, _prune_optimizer!) and `repeat(x[:, mask], 1, n_split)`
+ * (densify_split!, :83-94).  A row is row_bytes (multiple of 4) contiguous bytes: parameters, Adam moments,
+ * statistics and ids alike. */
+GSR_API int gsr_gather_rows(int64_t n, int32_t row_bytes, const void *src_dev, const uint8_t *mask_dev,
+                            const int32_t *offsets_dev, void *dst_dev, int32_t repeat, int64_t count, void *stream);
+/* The children of a split, in place on the gathered + repeated arrays of m new Gaussians: stds = exp(scales);
+ * points += R(q) * (stds .* noise) (`_add_split_noise!`, :123-136); scales = log(stds / (0.8 * n_split)) (:91).
+ * noise (3,m): N(0,1) samples supplied by the caller (the reference draws them from the device RNG in the kernel). */
+GSR_API int gsr_split_children(int64_t m, float *points_dev, float *scales_dev, int32_t isotropic,
+                               const float *rotations_dev, const float *noise_dev, int32_t n_split, void *stream);
 
 /* ---- the loss either side of the path ------------------------------------------------
  * Fused SSIM.  Arrays are the reference's (W,H,CH,B) column-major Float32, i.e. planar [b][c][y][x]; any W, H
