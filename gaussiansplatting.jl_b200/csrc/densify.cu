@@ -11,8 +11,8 @@
 //   split_children_kernel  `_add_split_noise!` + the children's log-scales             densification.jl:83-95,123-136
 // Byte movement is exact; exp / log / sigmoid are the same libdevice functions the fused-activation path uses.
 // The normal deviates of the split are an INPUT (the reference draws them from the device RNG inside the kernel,
-// which no other implementation can reproduce): the caller supplies N(0,1) samples, parity tests supply the same ones
-// to the oracle.
+// which no other implementation can reproduce): the caller supplies N(0,1) samples, and parity tests feed the same
+// samples to both sides.
 #include "common.cuh"
 
 namespace {
