@@ -46,3 +46,20 @@ gg = ssim.ssim_backward(x, t, torch.rand_like(x), d0, d1, d2)
 torch.cuda.synchronize()
 print("ssim", float(m.mean()), float(gg.abs().sum()))
 print("done 2")
+
+# densification kernels
+from gsrast import densify
+n = 3000
+rng = np.random.default_rng(2)
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+f = lambda *s: rng.normal(0, 1, s).astype(np.float32)
+model = dict(points=t(f(n, 3)), features_dc=t(f(n, 1, 3)), features_rest=t(f(n, 15, 3)), scales=t(rng.normal(-3, 1, (n, 3)).astype(np.float32)),
+             rotations=t(f(n, 4)), opacities=t(rng.normal(0, 3, (n, 1)).astype(np.float32)), ids=t(np.arange(n, dtype=np.int32)))
+opt = {k: (torch.randn_like(model[k]), torch.rand_like(model[k])) for k in densify.PARAMS}
+den = t(rng.integers(0, 4, n).astype(np.float32))
+stats = dict(max_radii=t(rng.integers(0, 40, n).astype(np.int32)), accum=t((rng.random(n) * 8e-4).astype(np.float32)) * (den > 0), denom=den)
+m, o, s, info = densify.densify_and_prune(model, opt, stats, grad_threshold=2e-4, dense_percent=0.01, extent=4.0, pruning_extent=4.0,
+                                          max_screen_size=20, min_opacity=0.005, noise=torch.randn((2 * n, 3), device="cuda"))
+torch.cuda.synchronize()
+print("densify", info, tuple(m["points"].shape))
+print("done 3")
