@@ -106,3 +106,24 @@ def test_photometric_loss_pullback_matches_finite_differences():  # training.jl:
         im[idx] -= eps
         fd = (o.photometric_loss(ip, tgt, 0.2)[0] - o.photometric_loss(im, tgt, 0.2)[0]) / (2 * eps)
         assert v[idx] == pytest.approx(fd, rel=1e-4, abs=1e-9)
+
+
+def test_ssim_structural_properties():
+    """Facts any correct SSIM restatement satisfies: symmetric in its arguments, 1 on identical inputs, <= 1, and the
+    pullback of sum(map) w.r.t. img at img == ref vanishes (a maximum).  fp64 build."""
+    rng = np.random.default_rng(23)
+    o = Oracle(np.float64)
+    for shape in [(1, 1, 12, 17), (2, 3, 30, 9)]:
+        x, y = rng.random(shape), rng.random(shape)
+        mxy = o.fused_ssim(x, y, train=False)[0]
+        myx = o.fused_ssim(y, x, train=False)[0]
+        assert np.abs(mxy - myx).max() < 1e-12
+        assert mxy.max() <= 1.0 + 1e-12
+        m, d0, d1, d2 = o.fused_ssim(x, x, train=True)
+        assert np.abs(m - 1.0).max() < 1e-12
+        g = o.fused_ssim_bwd(x, x, np.ones(shape), d0, d1, d2)
+        assert np.abs(g).max() < 1e-9
+    # zero padding: a constant image is NOT constant-SSIM near the border against a different constant
+    a, b = np.full((1, 1, 16, 16), 0.8), np.full((1, 1, 16, 16), 0.4)
+    m = o.fused_ssim(a, b, train=False)[0][0, 0]
+    assert abs(m[8, 8] - m[8, 7]) < 1e-12 and abs(m[0, 0] - m[8, 8]) > 1e-3
