@@ -9,11 +9,16 @@
 #include <cstring>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges are no-ops unless a profiler injects itself
+
 #include "common.cuh"
 
 namespace {
 
 std::atomic<int64_t> g_launches{0};
+const char *const kStageNames[GSR_NUM_STAGES] = {"gsr:preprocess", "gsr:scan",       "gsr:duplicate",
+                                                 "gsr:sort",       "gsr:ranges",     "gsr:render_fwd",
+                                                 "gsr:zero_grads", "gsr:render_bwd", "gsr:gauss_bwd"};
 thread_local std::string g_create_error;
 
 struct DevBuf {
@@ -57,6 +62,7 @@ struct GsrHandle {
     // state of the last forward
     int64_t last_n = 0, last_m = 0;
     bool fwd_valid = false;
+    int64_t generation = 0;  // bumped by every forward: a backward belongs to exactly one of them
 
     // per-stage timing
     bool profile = false;
@@ -134,9 +140,26 @@ void free_geometry(GsrHandle *h) {
     h->cap_n = 0;
 }
 
-int ensure_geometry(GsrHandle *h, int64_t n) {
+int ensure_geometry_alloc(GsrHandle *h, int64_t n, cudaStream_t s);
+
+// Grow-only GeometryState.  A failed growth releases whatever it had allocated (the byte accounting of
+// gsr_memory_usage stays exact) and leaves the handle without geometry buffers.
+int ensure_geometry(GsrHandle *h, int64_t n, cudaStream_t s) {
     if (n <= h->cap_n) return GSR_OK;
     free_geometry(h);  // rasterizer.jl:275-278: a larger scene replaces the whole GeometryState
+    if (h->gacc_external && h->gacc_external_cap < n)
+        return fail(h, GSR_EINVAL, "external accumulator smaller than the scene");
+    h->cap_n = n;  // free_geometry() releases by capacity: set it before the first allocation
+    const int rc = ensure_geometry_alloc(h, n, s);
+    if (rc != GSR_OK) {
+        const std::string msg = h->err;
+        free_geometry(h);
+        h->err = msg;
+    }
+    return rc;
+}
+
+int ensure_geometry_alloc(GsrHandle *h, int64_t n, cudaStream_t s) {
     const size_t c = (size_t)n;
     const int ch = h->cfg.channels;
     CK(dev_alloc(h, &h->g.depths, c));
@@ -151,23 +174,23 @@ int ensure_geometry(GsrHandle *h, int64_t n) {
     if (ch > 5) CK(dev_alloc(h, &h->g.normals, 3 * c));
     CK(dev_alloc(h, &h->g.rec, (size_t)rec_quads(ch) * c));
     if (h->gacc_external) {
-        if (h->gacc_external_cap < n) return fail(h, GSR_EINVAL, "external accumulator smaller than the scene");
         h->g.gacc = h->gacc_external;
     } else {
         CK(dev_alloc(h, &h->g.gacc, (size_t)acc_floats(ch) * c));
     }
     h->scan_cap = scan_state_words(n);
     CK(dev_alloc(h, &h->scan_state, 2 * h->scan_cap));
-    h->cap_n = n;
-    // KA.zeros in the reference (states.jl:30-47): stale-state reads of never-visible rows see zeros
-    CK(cudaMemset(h->g.depths, 0, c * 4));
-    CK(cudaMemset(h->g.means2d, 0, c * 8));
-    CK(cudaMemset(h->g.grad_means2d, 0, c * 8));
-    CK(cudaMemset(h->g.rgbs, 0, c * 12));
-    CK(cudaMemset(h->g.clamped, 0, c * 3));
-    CK(cudaMemset(h->g.conics, 0, c * 12));
-    CK(cudaMemset(h->g.radii, 0, c * 4));
-    if (ch > 5) CK(cudaMemset(h->g.normals, 0, c * 12));
+    // KA.zeros in the reference (states.jl:30-47): stale-state reads of never-visible rows see zeros.  Enqueued on
+    // the caller's stream: a legacy-stream cudaMemset is not ordered against a cudaStreamNonBlocking stream (torch
+    // side streams) and could land after this forward's preprocess kernel.
+    CK(cudaMemsetAsync(h->g.depths, 0, c * 4, s));
+    CK(cudaMemsetAsync(h->g.means2d, 0, c * 8, s));
+    CK(cudaMemsetAsync(h->g.grad_means2d, 0, c * 8, s));
+    CK(cudaMemsetAsync(h->g.rgbs, 0, c * 12, s));
+    CK(cudaMemsetAsync(h->g.clamped, 0, c * 3, s));
+    CK(cudaMemsetAsync(h->g.conics, 0, c * 12, s));
+    CK(cudaMemsetAsync(h->g.radii, 0, c * 4, s));
+    if (ch > 5) CK(cudaMemsetAsync(h->g.normals, 0, c * 12, s));
     return GSR_OK;
 }
 
@@ -224,9 +247,11 @@ struct StageTimer {  // records an event pair around a stage when profiling is o
     cudaStream_t s;
     int stage;
     StageTimer(GsrHandle *h_, cudaStream_t s_, int stage_) : h(h_), s(s_), stage(stage_) {
+        nvtxRangePushA(kStageNames[stage]);  // one NVTX range per stage (host-side launch span)
         if (h->profile) cudaEventRecord(h->ev[2 * stage], s);
     }
     ~StageTimer() {
+        nvtxRangePop();
         if (h->profile) {
             cudaEventRecord(h->ev[2 * stage + 1], s);
             h->ev_used[stage] = true;
@@ -252,6 +277,8 @@ const char *gsr_version(void) { return "gsrast 0.1.0 (sm_100a)"; }
 const char *gsr_last_error(const GsrHandle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int64_t gsr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int64_t gsr_forward_generation(const GsrHandle *h) { return h ? h->generation : -1; }
 
 int gsr_create(const GsrConfig *cfg, GsrHandle **out) {
     GsrHandle *h = nullptr;
@@ -286,6 +313,8 @@ int gsr_create(const GsrConfig *cfg, GsrHandle **out) {
         if ((e = cudaMemset(h->ranges, 0, 2 * (size_t)h->n_tiles * 4)) != cudaSuccess) break;
         if ((e = cudaMemset(h->n_contrib, 0, px * 4)) != cudaSuccess) break;
         if ((e = cudaMemset(h->accum_alpha, 0, px * 4)) != cudaSuccess) break;
+        // the fills ran on the legacy stream; later work arrives on caller streams that may be non-blocking
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
     } while (0);
     if (e != cudaSuccess) {
         rc = cuda_fail(nullptr, e, "gsr_create allocation");
@@ -326,8 +355,10 @@ int gsr_destroy(GsrHandle *h) {
     for (cudaEvent_t e : h->ev)
         if (e) cudaEventDestroy(e);
     for (auto &sl : h->slot)
-        for (cudaEvent_t e : {sl.h2d_done, sl.compute_done, sl.d2h_done})
+        for (cudaEvent_t e : {sl.h2d_done, sl.compute_done, sl.d2h_done, sl.t_h2d0, sl.t_h2d1, sl.t_c0, sl.t_c1, sl.t_d0,
+                              sl.t_d1})
             if (e) cudaEventDestroy(e);
+    if (h->t_base) cudaEventDestroy(h->t_base);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     delete h;
@@ -381,9 +412,10 @@ static int forward_impl(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t s
     const int ch = h->cfg.channels;
     const size_t image_bytes = (size_t)ch * h->cfg.width * h->cfg.height * sizeof(float);
     h->fwd_valid = false;
+    h->generation++;
     if (n_rendered) *n_rendered = 0;
 
-    int rc = ensure_geometry(h, n);
+    int rc = ensure_geometry(h, n, s);
     if (rc) return rc;
     DevCamera dc;
     make_dev_camera(h, cam, &dc);
@@ -497,11 +529,12 @@ static int backward_impl(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t 
     const int ch = h->cfg.channels;
     DevCamera dc;
     make_dev_camera(h, cam, &dc);
+    {   // always: a Gaussian can have radius > 0 and no tile (get_rect yields x1 == x0), so the per-Gaussian backward
+        // reads accumulator rows even when no instance was emitted
+        StageTimer tm(h, s, GSR_STAGE_ZERO_GRADS);
+        CK(cudaMemsetAsync(h->g.gacc, 0, (size_t)n * acc_floats(ch) * sizeof(float), s));
+    }
     if (h->last_m > 0) {
-        {
-            StageTimer tm(h, s, GSR_STAGE_ZERO_GRADS);
-            CK(cudaMemsetAsync(h->g.gacc, 0, (size_t)n * acc_floats(ch) * sizeof(float), s));
-        }
         StageTimer tm(h, s, GSR_STAGE_RENDER_BWD);
         float bg[8] = {background[0], background[1], background[2], 0.f, 0.f, 0.f, 0.f, 0.f};
         launch_render_backward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,

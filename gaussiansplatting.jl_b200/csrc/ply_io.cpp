@@ -233,8 +233,16 @@ void gsr_ply_close(void *reader) {
 
 int gsr_ply_write(const char *path, int64_t n, int32_t n_rest_coeffs, const float *points, const float *features_dc,
                   const float *features_rest, const float *opacities, const float *scales, const float *rotations) {
+    return gsr_ply_write_scales(path, n, n_rest_coeffs, 3, points, features_dc, features_rest, opacities, scales, rotations);
+}
+
+int gsr_ply_write_scales(const char *path, int64_t n, int32_t n_rest_coeffs, int32_t n_scale_rows, const float *points,
+                         const float *features_dc, const float *features_rest, const float *opacities,
+                         const float *scales, const float *rotations) {
     if (!path || n < 0 || n_rest_coeffs < 0) return fail("gsr_ply_write: bad argument");
-    const int R = n_rest_coeffs;
+    // export_ply writes one scale_i per row of `scales` (gaussians.jl:176): (3,N) or the isotropic (1,N)
+    if (n_scale_rows != 1 && n_scale_rows != 3) return fail("gsr_ply_write: scales must be (3,N) or isotropic (1,N)");
+    const int R = n_rest_coeffs, S = n_scale_rows;
     if (n > 0 && (!points || !features_dc || !opacities || !scales || !rotations || (R > 0 && !features_rest)))
         return fail("gsr_ply_write: null input");
     FILE *f = fopen(path, "wb");
@@ -246,10 +254,10 @@ int gsr_ply_write(const char *path, int64_t n, int32_t n_rest_coeffs, const floa
     for (int i = 0; i < 3; i++) fprintf(f, "property float f_dc_%d\n", i);
     for (int i = 0; i < 3 * R; i++) fprintf(f, "property float f_rest_%d\n", i);
     fprintf(f, "property float opacity\n");
-    for (int i = 0; i < 3; i++) fprintf(f, "property float scale_%d\n", i);
+    for (int i = 0; i < S; i++) fprintf(f, "property float scale_%d\n", i);
     for (int i = 0; i < 4; i++) fprintf(f, "property float rot_%d\n", i);
     fprintf(f, "end_header\n");
-    const int row = 3 + 3 + 3 + 3 * R + 1 + 3 + 4;
+    const int row = 3 + 3 + 3 + 3 * R + 1 + S + 4;
     const int64_t chunk = 4096;
     std::vector<float> buf((size_t)row * chunk);
     for (int64_t i0 = 0; i0 < n; i0 += chunk) {
@@ -263,8 +271,8 @@ int gsr_ply_write(const char *path, int64_t n, int32_t n_rest_coeffs, const floa
             for (int c = 0; c < 3; c++)
                 for (int k = 0; k < R; k++) o[9 + c * R + k] = features_rest[(size_t)i * 3 * R + c + 3 * k];
             o[9 + 3 * R] = opacities[i];
-            for (int k = 0; k < 3; k++) o[10 + 3 * R + k] = scales[3 * i + k];
-            for (int k = 0; k < 4; k++) o[13 + 3 * R + k] = rotations[4 * i + k];
+            for (int k = 0; k < S; k++) o[10 + 3 * R + k] = scales[S * i + k];
+            for (int k = 0; k < 4; k++) o[10 + S + 3 * R + k] = rotations[4 * i + k];
         }
         if (fwrite(buf.data(), sizeof(float) * row, (size_t)m, f) != (size_t)m) {
             fclose(f);

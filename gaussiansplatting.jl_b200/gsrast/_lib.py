@@ -36,32 +36,50 @@ class GsrStateViews(C.Structure):
 
 
 EXPORTS = ["gsr_version", "gsr_last_error", "gsr_create", "gsr_destroy", "gsr_release_scene_buffers",
-           "gsr_memory_usage", "gsr_get_state", "gsr_forward", "gsr_backward", "gsr_update_stats",
+           "gsr_memory_usage", "gsr_get_state", "gsr_forward_generation", "gsr_forward", "gsr_backward", "gsr_update_stats",
            "gsr_forward_backward_host", "gsr_identify_tile_range", "gsr_sort_pairs", "gsr_launch_count",
            "gsr_profile_enable", "gsr_profile_get", "gsr_measure_fp32_peak", "gsr_forward_backward_host_async",
            "gsr_host_wait", "gsr_host_timeline", "gsr_set_accumulator", "gsr_backward_render",
            "gsr_backward_gaussians_peers", "gsr_ssim_forward", "gsr_ssim_backward", "gsr_photometric_loss", "gsr_forward_raw", "gsr_backward_raw", "gsr_ply_open", "gsr_ply_read",
-           "gsr_ply_close", "gsr_ply_write", "gsr_ply_last_error", "gsr_densify_masks", "gsr_prune_mask",
+           "gsr_ply_close", "gsr_ply_write", "gsr_ply_write_scales", "gsr_ply_last_error", "gsr_densify_masks", "gsr_prune_mask",
            "gsr_mask_offsets_scratch_words", "gsr_mask_offsets", "gsr_gather_rows", "gsr_split_children"]
 STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "render_fwd", "zero_grads", "render_bwd", "gauss_bwd"]
 
 
+HASH_PATH = os.path.join(CSRC, "libgsrast.srchash")
+
+
+def _source_hash() -> str:
+    """sha256 over every file the library is built from (names + contents).  Content, not mtime: the snapshot that
+    travels to a GPU box does not preserve timestamps, and a rebuild there would burn GPU minutes."""
+    import hashlib
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h")) or f == "Makefile")
+    files.append(os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "gsrast.h"))
+    h = hashlib.sha256()
+    for f in files:
+        h.update(os.path.basename(f).encode() + b"\0")
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build(force: bool = False) -> str:
-    """Compile libgsrast.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
-    srcs.append(os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "gsrast.h"))
-    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
-    if force or stale:
+    """Compile libgsrast.so for sm_100a with nvcc (cross-compiles without a GPU) when it is missing or was built from
+    different sources (.cu / .cuh / .cpp / Makefile / include/gsrast.h)."""
+    want = _source_hash()
+    have = open(HASH_PATH).read().strip() if os.path.exists(HASH_PATH) else None
+    if force or not os.path.exists(LIB_PATH) or have != want:
         cmd = ["make", "-C", CSRC, "-j8"] + (["-B"] if force else [])
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("building libgsrast.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+        with open(HASH_PATH, "w") as fh:
+            fh.write(want + "\n")
     return LIB_PATH
 
 
 def load() -> C.CDLL:
-    if not os.path.exists(LIB_PATH):
-        build()
+    build()  # no-op unless the library is missing or stale with respect to its sources
     lib = C.CDLL(LIB_PATH)
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
     lib.gsr_version.restype = C.c_char_p
@@ -72,6 +90,8 @@ def load() -> C.CDLL:
     lib.gsr_release_scene_buffers.argtypes = [vp]
     lib.gsr_memory_usage.argtypes = [vp, C.POINTER(C.c_size_t)]
     lib.gsr_get_state.argtypes = [vp, C.POINTER(GsrStateViews)]
+    lib.gsr_forward_generation.argtypes = [vp]
+    lib.gsr_forward_generation.restype = i64
     lib.gsr_forward.argtypes = [vp, C.POINTER(GsrCamera), i64, i32, i32, vp, vp, vp, vp, vp, C.POINTER(C.c_float),
                                 vp, vp, vp, C.POINTER(i64), vp]
     lib.gsr_backward.argtypes = [vp, C.POINTER(GsrCamera), i64, i32, i32, vp, vp, vp, vp, vp, C.POINTER(C.c_float),
@@ -98,6 +118,7 @@ def load() -> C.CDLL:
     lib.gsr_ply_close.argtypes = [vp]
     lib.gsr_ply_close.restype = None
     lib.gsr_ply_write.argtypes = [C.c_char_p, i64, i32, vp, vp, vp, vp, vp, vp]
+    lib.gsr_ply_write_scales.argtypes = [C.c_char_p, i64, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.gsr_ply_last_error.restype = C.c_char_p
     lib.gsr_densify_masks.argtypes = [i64, i64, vp, vp, vp, i32, C.c_float, C.c_float, vp, vp, vp]
     lib.gsr_prune_mask.argtypes = [i64, vp, vp, i32, vp, C.c_float, i32, C.c_float, vp, vp]

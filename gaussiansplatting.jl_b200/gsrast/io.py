@@ -42,9 +42,12 @@ def save_ply(path: str, points, features_dc, features_rest, opacities, scales, r
     a = [np.ascontiguousarray(x, np.float32) for x in (points, features_dc, features_rest, opacities, scales, rotations)]
     N = a[0].shape[0]
     R = a[2].shape[1] if a[2].ndim == 3 else 0
-    assert a[0].shape == (N, 3) and a[1].shape == (N, 1, 3) and a[3].size == N and a[4].shape == (N, 3) and a[5].shape == (N, 4)
-    _check(_lib.lib().gsr_ply_write(str(path).encode(), N, R, _p(a[0]), _p(a[1]), _p(a[2]) if R and N else None, _p(a[3]), _p(a[4]),
-                                    _p(a[5])))
+    assert a[0].shape == (N, 3) and a[1].shape == (N, 1, 3) and a[3].size == N and a[5].shape == (N, 4)
+    if a[4].ndim != 2 or a[4].shape[0] != N or a[4].shape[1] not in (1, 3):
+        raise ValueError("scales must be (N,3) or, for an isotropic model, (N,1)")
+    S = a[4].shape[1]  # isotropic models carry one log-scale: export_ply then writes only scale_0 (gaussians.jl:176)
+    _check(_lib.lib().gsr_ply_write_scales(str(path).encode(), N, R, S, _p(a[0]), _p(a[1]), _p(a[2]) if R and N else None,
+                                           _p(a[3]), _p(a[4]), _p(a[5])))
 
 
 # ---- checkpoints (src/checkpoint.jl): safetensors files, structure in the dotted names, scalars in `__metadata__` ----

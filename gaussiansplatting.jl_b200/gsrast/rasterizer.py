@@ -312,6 +312,19 @@ class GaussianRasterizer:
             check(_lib.lib().gsr_backward_gaussians_peers(self._h, world, rank, cams, ga, tb, n, sh_degree, K, _ptr(means),
                                                           _ptr(shs), _ptr(opac), _ptr(scales), _ptr(rots), stream), self._h)
 
+    def forward_generation(self) -> int:
+        """Number of forwards this handle has run (gsr_forward_generation)."""
+        return int(_lib.lib().gsr_forward_generation(self._h))
+
+    def _check_generation(self, gen: int):
+        """The handle keeps the per-pixel / binning state of its LAST forward only (as rast.{g,b,i}state do in the
+        reference): a backward whose forward has since been overwritten would silently differentiate the wrong view."""
+        now = self.forward_generation()
+        if now != gen:
+            raise RuntimeError(f"rasterize backward: the rasterizer ran {now - gen} more forward(s) after the one being "
+                               "differentiated; its state was overwritten. Call backward before the next forward on "
+                               "this GaussianRasterizer, or use one rasterizer per in-flight view.")
+
     def host_wait(self):
         check(_lib.lib().gsr_host_wait(self._h), self._h)
 
@@ -343,11 +356,13 @@ class _Rasterize(torch.autograd.Function):
         rast.image = image
         ctx.save_for_backward(means, shs, opac, scales, rots, Rc, tc)
         ctx.rast, ctx.camera, ctx.sh_degree, ctx.background = rast, camera, sh_degree, background
+        ctx.generation = rast.forward_generation()
         return image
 
     @staticmethod
     def backward(ctx, vpixels):
         means, shs, opac, scales, rots, Rc, tc = ctx.saved_tensors
+        ctx.rast._check_generation(ctx.generation)
         g = ctx.rast._backward(vpixels.contiguous(), means, shs, opac, scales, rots, Rc, tc, ctx.camera, ctx.sh_degree,
                                ctx.background)
         return (g["vmeans"], g["vshs"], g["vopacities"].view_as(opac), g["vscales"], g["vrot"], g["vR"], g["vt"],
@@ -371,11 +386,13 @@ class _RasterizeRaw(torch.autograd.Function):
         rast.image = image
         ctx.save_for_backward(means, opac, scales, rots, dc, rest, Rc, tc)
         ctx.rast, ctx.camera, ctx.sh_degree, ctx.background = rast, camera, sh_degree, background
+        ctx.generation = rast.forward_generation()
         return image
 
     @staticmethod
     def backward(ctx, vpixels):
         means, opac, scales, rots, dc, rest, Rc, tc = ctx.saved_tensors
+        ctx.rast._check_generation(ctx.generation)
         g = ctx.rast._raw_call(True, means, opac, scales, rots, dc, rest, Rc, tc, ctx.camera, ctx.sh_degree,
                                ctx.background, vpixels=vpixels.contiguous())
         return (g["vmeans"], g["vopacities"].view_as(opac), g["vscales"], g["vrot"], g["vfeatures_dc"],

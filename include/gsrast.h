@@ -114,6 +114,10 @@ GSR_API int gsr_release_scene_buffers(GsrHandle *h);
 /* memory_usage(rast) — rasterizer.jl:127-134 (workspace bytes owned by the handle) */
 GSR_API int gsr_memory_usage(const GsrHandle *h, size_t *bytes);
 GSR_API int gsr_get_state(const GsrHandle *h, GsrStateViews *views);
+/* Number of forwards this handle has run.  gsr_backward differentiates the LAST forward (its per-pixel and binning
+ * state live in the handle, as rast.{g,b,i}state do in the reference): a caller that interleaves forwards keeps the
+ * value returned after its forward and compares before its backward (the Python mirror and the Julia shim raise). */
+GSR_API int64_t gsr_forward_generation(const GsrHandle *h);
 
 /* rasterize(...) — rasterizer.jl:255-408.
  *   n, K          Gaussians, stored SH coefficients per Gaussian ((max_sh_degree+1)^2); sh_degree in [0,3]
@@ -286,6 +290,11 @@ GSR_API void gsr_ply_close(void *reader);
 GSR_API int gsr_ply_write(const char *path, int64_t n, int32_t n_rest_coeffs, const float *points,
                           const float *features_dc, const float *features_rest, const float *opacities,
                           const float *scales, const float *rotations);
+/* Same, with the row count of `scales` stated: 3 = (3,N); 1 = an isotropic model's (1,N), for which export_ply emits
+ * only `scale_0` (gaussians.jl:176 iterates axes(scales,1)).  gsr_ply_write is the n_scale_rows = 3 case. */
+GSR_API int gsr_ply_write_scales(const char *path, int64_t n, int32_t n_rest_coeffs, int32_t n_scale_rows,
+                                 const float *points, const float *features_dc, const float *features_rest,
+                                 const float *opacities, const float *scales, const float *rotations);
 GSR_API const char *gsr_ply_last_error(void);
 
 /* Per-stage device timing (CUDA events on the caller's stream; SURVEY.md §5 "tracing / profiling").

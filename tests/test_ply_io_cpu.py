@@ -125,3 +125,22 @@ def test_reader_errors(tmp_path):
     open(p, "wb").write(b"not a ply\n")
     with pytest.raises(_lib.GsrError, match="not a PLY"):
         io.load_ply(p)
+
+
+def test_isotropic_model_writes_scale_0_only(tmp_path):
+    """export_ply iterates axes(scales,1) (gaussians.jl:176): an isotropic (1,N) model gets `scale_0` only; the
+    3-row writer must not be handed a 1-row array (it would read past the buffer)."""
+    io = _io()
+    m = model(300, 3, 5)
+    m["scales"] = m["scales"][:, :1].copy()
+    p = str(tmp_path / "iso.ply")
+    io.save_ply(p, **m)
+    raw = open(p, "rb").read()
+    head, data = raw.split(b"end_header\n", 1)
+    props = [l.split()[2].decode() for l in head.split(b"\n") if l.startswith(b"property")]
+    assert [q for q in props if q.startswith("scale_")] == ["scale_0"]
+    a = np.frombuffer(data, "<f4").reshape(300, len(props))
+    assert np.array_equal(a[:, props.index("scale_0")], m["scales"][:, 0])
+    assert np.array_equal(a[:, props.index("rot_3")], m["rotations"][:, 3])
+    with pytest.raises(ValueError):
+        io.save_ply(p, **{**m, "scales": np.zeros((300, 2), np.float32)})
