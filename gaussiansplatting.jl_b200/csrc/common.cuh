@@ -86,13 +86,16 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
 
 void launch_tile_ranges(int64_t m, const uint64_t *keys_sorted, uint32_t *ranges, cudaStream_t s);
 
-void launch_render_forward(int channels, int math_mode, int width, int height, const uint32_t *ranges,
-                           const uint32_t *vals_sorted, const float4 *rec, const float *bg, float *image,
-                           uint32_t *n_contrib, float *accum_alpha, uint8_t *covis, float *uncert, cudaStream_t s);
+// both return 0, or -1 when no kernel was compiled for `math_mode`
+int launch_render_forward(int channels, int math_mode, int width, int height, const uint32_t *ranges,
+                          const uint32_t *vals_sorted, const float4 *rec, const float *bg, float *image,
+                          uint32_t *n_contrib, float *accum_alpha, uint8_t *covis, float *uncert, cudaStream_t s);
 
-void launch_render_backward(int channels, int math_mode, int width, int height, const uint32_t *ranges,
-                            const uint32_t *vals_sorted, const float4 *rec, const float *bg, const float *vpixels,
-                            const uint32_t *n_contrib, const float *accum_alpha, float *gacc, cudaStream_t s);
+int launch_render_backward(int channels, int math_mode, int width, int height, const uint32_t *ranges,
+                           const uint32_t *vals_sorted, const float4 *rec, const float *bg, const float *vpixels,
+                           const uint32_t *n_contrib, const float *accum_alpha, float *gacc, cudaStream_t s);
+int render_math_mode_supported(int math_mode);
+int launch_exp_neg_probe(const float *sigma, float *split, float *libdev, int64_t n, cudaStream_t s);
 
 void launch_backward_gaussians(const DevCamera &cam, int64_t n, int sh_degree, int K, int channels,
                                const float *means, const float *shs, const float *opac, const float *scales,

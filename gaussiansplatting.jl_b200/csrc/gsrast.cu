@@ -288,8 +288,8 @@ int gsr_create(const GsrConfig *cfg, GsrHandle **out) {
         return fail(h, GSR_EINVAL, "width and height must be positive multiples of 16 (rasterizer.jl:66)");
     if (cfg->channels != 3 && cfg->channels != 5 && cfg->channels != 8)
         return fail(h, GSR_EINVAL, "Invalid render mode: channels must be 3 (:rgb), 5 (:rgbd) or 8 (:rgbdn)");
-    if (cfg->math_mode != GSR_MATH_REFERENCE && cfg->math_mode != GSR_MATH_FAST)
-        return fail(h, GSR_EINVAL, "math_mode must be GSR_MATH_REFERENCE or GSR_MATH_FAST");
+    if (!render_math_mode_supported(cfg->math_mode))
+        return fail(h, GSR_EINVAL, "math_mode must be GSR_MATH_STRICT, GSR_MATH_REFERENCE or GSR_MATH_FAST");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -465,8 +465,9 @@ static int forward_impl(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t s
     {
         StageTimer tm(h, s, GSR_STAGE_RENDER_FWD);
         float bg[8] = {background[0], background[1], background[2], 0.f, 0.f, 0.f, 0.f, 0.f};  // rasterizer.jl:411-414
-        launch_render_forward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,
-                              bg, image_out, h->n_contrib, h->accum_alpha, covis, uncert, s);
+        if (launch_render_forward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,
+                                  bg, image_out, h->n_contrib, h->accum_alpha, covis, uncert, s))
+            return fail(h, GSR_EINVAL, "no compositing kernel for this math_mode");
     }
     CK(cudaGetLastError());
     if (n_rendered) *n_rendered = m;
@@ -537,8 +538,9 @@ static int backward_impl(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t 
     if (h->last_m > 0) {
         StageTimer tm(h, s, GSR_STAGE_RENDER_BWD);
         float bg[8] = {background[0], background[1], background[2], 0.f, 0.f, 0.f, 0.f, 0.f};
-        launch_render_backward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,
-                               bg, vpixels, h->n_contrib, h->accum_alpha, h->g.gacc, s);
+        if (launch_render_backward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,
+                                   bg, vpixels, h->n_contrib, h->accum_alpha, h->g.gacc, s))
+            return fail(h, GSR_EINVAL, "no compositing kernel for this math_mode");
     }
     {
         StageTimer tm(h, s, GSR_STAGE_GAUSS_BWD);
@@ -597,8 +599,9 @@ int gsr_backward_render(GsrHandle *h, int64_t n, const float background[3], cons
     if (h->last_m > 0) {
         StageTimer tm(h, s, GSR_STAGE_RENDER_BWD);
         float bg[8] = {background[0], background[1], background[2], 0.f, 0.f, 0.f, 0.f, 0.f};
-        launch_render_backward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,
-                               bg, vpixels, h->n_contrib, h->accum_alpha, h->g.gacc, s);
+        if (launch_render_backward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,
+                                   bg, vpixels, h->n_contrib, h->accum_alpha, h->g.gacc, s))
+            return fail(h, GSR_EINVAL, "no compositing kernel for this math_mode");
     }
     launch_grad_means2d(n, ch, h->g.radii, h->g.conics, h->g.gacc, h->g.grad_means2d, s);
     CK(cudaGetLastError());
@@ -806,6 +809,11 @@ int gsr_profile_get(GsrHandle *h, float ms[GSR_NUM_STAGES]) {
         }
     }
     return GSR_OK;
+}
+
+int gsr_debug_exp_neg(const float *sigma_dev, float *split_dev, float *libdevice_dev, int64_t n, void *stream) {
+    if (n < 0 || (n > 0 && (!sigma_dev || !split_dev || !libdevice_dev))) return GSR_EINVAL;
+    return launch_exp_neg_probe(sigma_dev, split_dev, libdevice_dev, n, static_cast<cudaStream_t>(stream)) ? GSR_ECUDA : GSR_OK;
 }
 
 int gsr_measure_fp32_peak(double *tflops, void *stream) {

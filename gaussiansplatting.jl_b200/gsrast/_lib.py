@@ -14,7 +14,7 @@ CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 LIB_PATH = os.path.join(CSRC, "libgsrast.so")
 
 GSR_OK, GSR_EINVAL, GSR_ECUDA, GSR_ENOMEM, GSR_ESTATE = 0, -1, -2, -3, -4
-MATH_REFERENCE, MATH_FAST = 0, 1
+MATH_REFERENCE, MATH_FAST, MATH_STRICT, MATH_EXPERIMENT = 0, 1, 2, 256
 
 
 class GsrConfig(C.Structure):
@@ -38,7 +38,7 @@ class GsrStateViews(C.Structure):
 EXPORTS = ["gsr_version", "gsr_last_error", "gsr_create", "gsr_destroy", "gsr_release_scene_buffers",
            "gsr_memory_usage", "gsr_get_state", "gsr_forward_generation", "gsr_forward", "gsr_backward", "gsr_update_stats",
            "gsr_forward_backward_host", "gsr_identify_tile_range", "gsr_sort_pairs", "gsr_launch_count",
-           "gsr_profile_enable", "gsr_profile_get", "gsr_measure_fp32_peak", "gsr_forward_backward_host_async",
+           "gsr_profile_enable", "gsr_profile_get", "gsr_measure_fp32_peak", "gsr_debug_exp_neg", "gsr_forward_backward_host_async",
            "gsr_host_wait", "gsr_host_timeline", "gsr_set_accumulator", "gsr_backward_render",
            "gsr_backward_gaussians_peers", "gsr_ssim_forward", "gsr_ssim_backward", "gsr_photometric_loss", "gsr_forward_raw", "gsr_backward_raw", "gsr_ply_open", "gsr_ply_read",
            "gsr_ply_close", "gsr_ply_write", "gsr_ply_write_scales", "gsr_ply_last_error", "gsr_densify_masks", "gsr_prune_mask",
@@ -133,6 +133,7 @@ def load() -> C.CDLL:
     lib.gsr_profile_enable.argtypes = [vp, i32]
     lib.gsr_profile_get.argtypes = [vp, C.POINTER(C.c_float)]
     lib.gsr_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), vp]
+    lib.gsr_debug_exp_neg.argtypes = [vp, vp, vp, i64, vp]
     for name in EXPORTS:
         getattr(lib, name)  # every symbol of include/gsrast.h must resolve
     return lib

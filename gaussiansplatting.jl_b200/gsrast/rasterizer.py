@@ -122,7 +122,7 @@ class GaussianRasterizer:
     """`GaussianRasterizer(kab; width, height, mode, near_plane, far_plane)` — rasterizer.jl:60-90."""
 
     def __init__(self, *, width: int, height: int, mode: str = "rgbd", near_plane: float = 0.2,
-                 far_plane: float = 1000.0, device="cuda", math_mode: str = "fast"):
+                 far_plane: float = 1000.0, device="cuda", math_mode: str | int = "strict"):
         assert width % 16 == 0 and height % 16 == 0  # rasterizer.jl:66
         if mode not in MODES:
             raise ValueError(f"Invalid render: {mode} ∉ {tuple(MODES)}")  # rasterizer.jl:68
@@ -134,8 +134,12 @@ class GaussianRasterizer:
         self.device = torch.device(device)
         self.grid = (width // BLOCK, height // BLOCK)
         self.n_tiles = self.grid[0] * self.grid[1]
-        cfg = GsrConfig(width, height, self.channels, near_plane, far_plane, 3, 0.3,
-                        {"reference": _lib.MATH_REFERENCE, "fast": _lib.MATH_FAST}[math_mode])
+        # "strict" (default): meets the flat 1e-5 / 1e-4 tolerances; "reference": every op in the reference's order;
+        # "fast": log2-domain ex2.approx path with conditioning-dependent error; an int selects an A/B policy build
+        self.math_mode = math_mode
+        mm = math_mode if isinstance(math_mode, int) else {"reference": _lib.MATH_REFERENCE, "fast": _lib.MATH_FAST,
+                                                            "strict": _lib.MATH_STRICT}[math_mode]
+        cfg = GsrConfig(width, height, self.channels, near_plane, far_plane, 3, 0.3, mm)
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(_lib.lib().gsr_create(C.byref(cfg), C.byref(self._h)))

@@ -45,6 +45,7 @@ end
 
 const GSR_MATH_REFERENCE = Int32(0)
 const GSR_MATH_FAST = Int32(1)
+const GSR_MATH_STRICT = Int32(2)    # default: flat 1e-5 / 1e-4 parity with the reference
 
 function check(rc::Cint, h::Ptr{Cvoid} = C_NULL)
     rc == 0 && return
@@ -59,7 +60,7 @@ function handle(rast::GaussianRasterizer)
     get!(HANDLES, rast) do
         width, height = size(rast.image, 2), size(rast.image, 3)
         cfg = Ref(GsrConfig(width, height, n_color_features(rast.mode), rast.near_plane, rast.far_plane,
-                            Int32(3), 0.3f0, GSR_MATH_FAST))   # radius_clip, blur_ϵ: rasterizer.jl:294-295
+                            Int32(3), 0.3f0, GSR_MATH_STRICT))   # radius_clip, blur_ϵ: rasterizer.jl:294-295
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:gsr_create, libgsrast), Cint, (Ref{GsrConfig}, Ref{Ptr{Cvoid}}), cfg, out))
         finalizer(r -> ccall((:gsr_destroy, libgsrast), Cint, (Ptr{Cvoid},), pop!(HANDLES, r, C_NULL)), rast)

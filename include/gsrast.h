@@ -49,8 +49,16 @@ typedef enum {
 } GsrStatus;
 
 /* math_mode values */
-#define GSR_MATH_REFERENCE 0 /* compositing in the reference's op order, no FMA contraction, expf()      */
-#define GSR_MATH_FAST 1      /* contracted FMAs + ex2.approx in the compositing kernels (same tolerances) */
+#define GSR_MATH_REFERENCE 0 /* every compositing operation in the reference's op order: no FMA contraction, libdevice
+                                expf, IEEE division (render.jl:90-106, 237-263).  The cross-check build.            */
+#define GSR_MATH_FAST 1      /* log2-domain exponent, contracted FMAs, one ex2.approx.  Fastest; image error grows with
+                                the conditioning of a pixel (elongated / near-opaque Gaussians), so it is NOT held to
+                                the flat 1e-5.                                                                       */
+#define GSR_MATH_STRICT 2    /* DEFAULT.  sigma bit-exact in the reference's order, alpha = min(0.99, o expf(-sigma)) with
+                                libdevice's expf (what the reference's CUDA extension compiles exp to), depth-channel
+                                sums in the reference's order; cheaper forms only where the outputs are insensitive.  Meets 1e-5 absolute (image, depth) / 1e-4 relative
+                                (gradients) against the fp32 restatement of the reference.                           */
+#define GSR_MATH_EXPERIMENT 256 /* + policy word: A/B builds only (-DGSR_POLICY_AB), not a supported surface        */
 
 /* Constructor arguments of `GaussianRasterizer(kab; width, height, mode, near_plane, far_plane)`
  * (rasterizer.jl:60-90) plus the constants `rasterize` hard-codes (rasterizer.jl:294-295). */
@@ -318,6 +326,11 @@ GSR_API int gsr_profile_get(GsrHandle *h, float ms[GSR_NUM_STAGES]);
 /* FP32 FMA micro-benchmark on the current device (dependent FFMA chains, all SMs): the measured FP32 peak
  * that the compositing kernels' roofline fraction is quoted against. */
 GSR_API int gsr_measure_fp32_peak(double *tflops, void *stream);
+
+/* Test hook: exp(-sigma) as the A/B split policy evaluates it (one ex2.approx after a Cody-Waite split) and as
+ * GSR_MATH_REFERENCE does (libdevice expf), element-wise over n device floats; tests/ bound both against a correctly
+ * rounded exp. */
+GSR_API int gsr_debug_exp_neg(const float *sigma_dev, float *split_dev, float *libdevice_dev, int64_t n, void *stream);
 
 /* Kernels launched by this library since process start (bench.py's gpu_launches). */
 GSR_API int64_t gsr_launch_count(void);

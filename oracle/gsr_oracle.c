@@ -26,6 +26,9 @@
  *   Gaussian ids in `values` are 1-based, exactly as `duplicate_with_keys!` emits them.
  */
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -50,6 +53,18 @@ typedef float real;
 #define EXPORT __attribute__((visibility("default")))
 
 #define BLOCK 16 /* GaussianSplatting.jl:55-56 BLOCK = (16,16) */
+
+/* OpenMP team size of every stage below; returns the size in effect.  n <= 0 only queries.  (A launcher such as
+ * torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU baseline must not inherit that silently.) */
+EXPORT int orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 static inline real rmin_(real a, real b) { return a < b ? a : b; }
 static inline real rmax_(real a, real b) { return a > b ? a : b; }

@@ -109,6 +109,10 @@ class Oracle:
         self.lib.orc_cumsum.restype = C.c_int64
         self.lib.orc_gaussian_normal.restype = C.c_int32
 
+    def set_threads(self, n: int = 0) -> int:
+        """OpenMP team size of the C stages (n <= 0: query).  Returns the size in effect."""
+        return int(self.lib.orc_set_threads(int(n)))
+
     # ---------------------------------------------------------------- utils
     def arr(self, x, shape=None):
         a = np.ascontiguousarray(np.asarray(x, dtype=self.dtype))

@@ -37,7 +37,7 @@ def test_fused_activations_match_composed_path(K, deg, iso, mode):
     from gsrast import Camera, GaussianRasterizer
     sc, p = _scene(20_000, K, iso, 31 + K)
     cam = Camera(fx=sc.fx, fy=sc.fy, width=sc.width, height=sc.height)
-    rast = GaussianRasterizer(width=sc.width, height=sc.height, mode=mode, math_mode="reference")
+    rast = GaussianRasterizer(width=sc.width, height=sc.height, mode=mode)
     vpix = torch.randn((sc.height, sc.width, rast.channels), device="cuda") / (sc.width * sc.height)
     img_c, g_c = _run(rast, p, cam, deg, False, vpix, background=(0.1, 0.2, 0.3))
     radii_c = rast.gstate.radii.clone()

@@ -106,7 +106,7 @@ def test_loss_cotangent_feeds_the_rasterizer_backward():
     sc = make_scene(3000, 1, 128, 96, 77)
     cam, ocam = P.cameras(sc)
     dev = P.to_dev(sc)
-    rast = GaussianRasterizer(width=sc.width, height=sc.height, mode="rgbd", math_mode="reference")
+    rast = GaussianRasterizer(width=sc.width, height=sc.height, mode="rgbd")
     img = P.gpu_forward(rast, dev, cam, sc.sh_degree)
     tgt = np.random.default_rng(9).random((3, 96, 128), dtype=np.float32)
     loss, vpix = ssim.photometric_loss(rast, img, torch.from_numpy(tgt).cuda(), 0.2)
