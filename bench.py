@@ -190,7 +190,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="gsrast", choices=["gsrast", "reference"])
-    ap.add_argument("--math", default="fast", choices=["fast", "reference"])
+    ap.add_argument("--math", default="strict", choices=["strict", "reference", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--config", default="C2")

@@ -95,7 +95,7 @@ int launch_render_backward(int channels, int math_mode, int width, int height, c
                            const uint32_t *vals_sorted, const float4 *rec, const float *bg, const float *vpixels,
                            const uint32_t *n_contrib, const float *accum_alpha, float *gacc, cudaStream_t s);
 int render_math_mode_supported(int math_mode);
-int launch_exp_neg_probe(const float *sigma, float *split, float *libdev, int64_t n, cudaStream_t s);
+int launch_exp_neg_probe(const float *sigma, float *split, float *libdev, float *inlined, int64_t n, cudaStream_t s);
 
 void launch_backward_gaussians(const DevCamera &cam, int64_t n, int sh_degree, int K, int channels,
                                const float *means, const float *shs, const float *opac, const float *scales,

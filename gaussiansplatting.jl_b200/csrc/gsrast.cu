@@ -811,9 +811,10 @@ int gsr_profile_get(GsrHandle *h, float ms[GSR_NUM_STAGES]) {
     return GSR_OK;
 }
 
-int gsr_debug_exp_neg(const float *sigma_dev, float *split_dev, float *libdevice_dev, int64_t n, void *stream) {
+int gsr_debug_exp_neg(const float *sigma_dev, float *split_dev, float *libdevice_dev, float *inlined_dev, int64_t n,
+                      void *stream) {
     if (n < 0 || (n > 0 && (!sigma_dev || !split_dev || !libdevice_dev))) return GSR_EINVAL;
-    return launch_exp_neg_probe(sigma_dev, split_dev, libdevice_dev, n, static_cast<cudaStream_t>(stream)) ? GSR_ECUDA : GSR_OK;
+    return launch_exp_neg_probe(sigma_dev, split_dev, libdevice_dev, inlined_dev, n, static_cast<cudaStream_t>(stream)) ? GSR_ECUDA : GSR_OK;
 }
 
 int gsr_measure_fp32_peak(double *tflops, void *stream) {

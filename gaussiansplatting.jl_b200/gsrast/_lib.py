@@ -79,8 +79,10 @@ def build(force: bool = False) -> str:
 
 
 def load() -> C.CDLL:
-    build()  # no-op unless the library is missing or stale with respect to its sources
-    lib = C.CDLL(LIB_PATH)
+    override = os.environ.get("GSRAST_LIB")  # A/B builds of the same sources with other -D flags (tools/ only)
+    if not override:
+        build()  # no-op unless the library is missing or stale with respect to its sources
+    lib = C.CDLL(override or LIB_PATH)
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
     lib.gsr_version.restype = C.c_char_p
     lib.gsr_last_error.restype = C.c_char_p
@@ -133,7 +135,7 @@ def load() -> C.CDLL:
     lib.gsr_profile_enable.argtypes = [vp, i32]
     lib.gsr_profile_get.argtypes = [vp, C.POINTER(C.c_float)]
     lib.gsr_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), vp]
-    lib.gsr_debug_exp_neg.argtypes = [vp, vp, vp, i64, vp]
+    lib.gsr_debug_exp_neg.argtypes = [vp, vp, vp, vp, i64, vp]
     for name in EXPORTS:
         getattr(lib, name)  # every symbol of include/gsrast.h must resolve
     return lib

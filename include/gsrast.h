@@ -327,10 +327,11 @@ GSR_API int gsr_profile_get(GsrHandle *h, float ms[GSR_NUM_STAGES]);
  * that the compositing kernels' roofline fraction is quoted against. */
 GSR_API int gsr_measure_fp32_peak(double *tflops, void *stream);
 
-/* Test hook: exp(-sigma) as the A/B split policy evaluates it (one ex2.approx after a Cody-Waite split) and as
- * GSR_MATH_REFERENCE does (libdevice expf), element-wise over n device floats; tests/ bound both against a correctly
- * rounded exp. */
-GSR_API int gsr_debug_exp_neg(const float *sigma_dev, float *split_dev, float *libdevice_dev, int64_t n, void *stream);
+/* Test hook: exp(-sigma) three ways, element-wise over n device floats — the A/B split policy (one ex2.approx after a
+ * Cody-Waite split), libdevice's expf, and the inlined instruction sequence GSR_MATH_STRICT uses (may be NULL), which
+ * tests/ require to equal libdevice's expf bit for bit. */
+GSR_API int gsr_debug_exp_neg(const float *sigma_dev, float *split_dev, float *libdevice_dev, float *inlined_dev, int64_t n,
+                              void *stream);
 
 /* Kernels launched by this library since process start (bench.py's gpu_launches). */
 GSR_API int64_t gsr_launch_count(void);
