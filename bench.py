@@ -92,9 +92,14 @@ class ClockSampler:
 def stage_bytes(N, V, M, T, P, C, K, k):
     """ALGORITHMIC bytes per stage and step — SURVEY.md §8(d)."""
     Cp = C if C > 3 else 3
-    b = round(np.ceil(np.log2(max(T, 2)))) + 27  # significant key bits (Appendix A.4)
-    passes = int(np.ceil(b / 8))
+    tile_bits, depth_bits = int(np.ceil(np.log2(max(T, 2)))), 27  # significant key bits (Appendix A.4)
+    presort = os.environ.get("GSR_PRESORT", "1") != "0"
+    # depth pre-sort (default): 4 radix passes over the N Gaussians' (depth, index) pairs, then only the tile digits
+    # over the M instances; without it every significant bit is sorted over M
+    passes = int(np.ceil(tile_bits / 8)) if presort else int(np.ceil((tile_bits + depth_bits) / 8))
+    ppasses = int(np.ceil((1 + depth_bits) / 8))
     return {
+        "presort": (8 * N + 12 * N + 8 * N + 24 * N * ppasses) if presort else 0,
         "preprocess": 40 * N + 4 * N + V * (12 * k + 28 + 4 * Cp + 3 + 4),
         "scan": 8 * N,
         "duplicate": 20 * V + 12 * M,

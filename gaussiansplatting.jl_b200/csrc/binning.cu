@@ -14,6 +14,14 @@
 // keep emission order (ascending Gaussian id), which the reference's sortperm! also guarantees.
 // The published buffers hold the canonical (tile << 32 | bits(depth)) keys and 1-based ids.
 //
+//
+// Depth pre-sort (default): every instance of a Gaussian carries the same depth, so sorting the M instances on the
+// depth digits re-sorts M keys on bits that only the N Gaussians distinguish.  Instead the Gaussians are sorted by
+// depth first (presort_keys_kernel + the same onesweep passes over N pairs), instances are emitted in that order
+// (scan and duplicate read through the permutation), and the instance sort runs over the tile digits only:
+// 2 passes over M + 4 over N instead of 5 over M at 1920x1088.  LSD radix sort is stable, so the result is the same
+// permutation bit for bit: (tile, depth, emission order = Gaussian id).
+//
 // All integer work: bit-exact by construction; compiled with default flags.
 #include <cstdlib>
 #include <cstring>
@@ -37,8 +45,9 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
     return *reinterpret_cast<const volatile uint32_t *>(p);
 }
 
+// perm != nullptr: element j of the scan is in[perm[j]] (tiles touched in depth order, see the pre-sort above)
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_kernel(const int64_t n, const int32_t *__restrict__ in, int32_t *__restrict__ out,
+scan_kernel(const int64_t n, const int32_t *__restrict__ in, const uint32_t *__restrict__ perm, int32_t *__restrict__ out,
             unsigned long long *state /* [0] = tile counter, [1..] = status */, int64_t *total) {
     __shared__ long long s_warp[SCAN_THREADS / 32];
     __shared__ long long s_prefix;
@@ -51,13 +60,18 @@ scan_kernel(const int64_t n, const int32_t *__restrict__ in, int32_t *__restrict
     const int64_t base = tile * SCAN_TILE + (int64_t)tid * SCAN_IPT;
 
     int32_t v[SCAN_IPT];
+    const int32_t *src = perm ? reinterpret_cast<const int32_t *>(perm) : in;
     if (base + SCAN_IPT <= n) {
-        const int4 a = *reinterpret_cast<const int4 *>(in + base);
-        const int4 b = *reinterpret_cast<const int4 *>(in + base + 4);
+        const int4 a = *reinterpret_cast<const int4 *>(src + base);
+        const int4 b = *reinterpret_cast<const int4 *>(src + base + 4);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else {
 #pragma unroll
-        for (int k = 0; k < SCAN_IPT; k++) v[k] = (base + k < n) ? in[base + k] : 0;
+        for (int k = 0; k < SCAN_IPT; k++) v[k] = (base + k < n) ? src[base + k] : 0;
+    }
+    if (perm) {  // eight independent gathers in flight
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++) v[k] = (base + k < n) ? __ldg(in + v[k]) : 0;
     }
     long long tsum = 0;
 #pragma unroll
@@ -136,35 +150,38 @@ constexpr int SORT_MAX_PASSES = 8;
 // Digit histograms of the radix sort are accumulated while the keys are generated (no extra pass over the M
 // keys): each thread emits ITS Gaussian's instances, so concurrent shared-memory atomics hit unrelated tiles
 // (low conflict); digits that lie entirely inside the depth bits are added once per Gaussian with weight cnt.
-__device__ __forceinline__ void hist_add_instance(uint32_t *sh, uint64_t ck, int first_pass, int passes) {
-    for (int p = first_pass; p < passes; p++) atomicAdd(&sh[p * 256 + (uint32_t)((ck >> (8 * p)) & 255u)], 1u);
+__device__ __forceinline__ void hist_add_instance(uint32_t *sh, uint64_t ck, int first_pass, int passes, int bit_lo) {
+    for (int p = first_pass; p < passes; p++) atomicAdd(&sh[p * 256 + (uint32_t)((ck >> (bit_lo + 8 * p)) & 255u)], 1u);
 }
 
 __global__ void __launch_bounds__(DUP_THREADS)
 duplicate_kernel(const int64_t n, const int32_t grid_x, const int32_t grid_y, const int32_t *__restrict__ radii,
                  const float2 *__restrict__ means2d, const float *__restrict__ depths,
-                 const int32_t *__restrict__ offsets, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                 const int depth_bits, const uint32_t depth_base, const int passes, uint32_t *__restrict__ ghist) {
+                 const int32_t *__restrict__ offsets, const uint32_t *__restrict__ perm, uint64_t *__restrict__ keys,
+                 uint32_t *__restrict__ vals, const int depth_bits, const uint32_t depth_base, const int bit_lo,
+                 const int passes, uint32_t *__restrict__ ghist) {
     __shared__ uint32_t sh[SORT_MAX_PASSES * 256];
     const bool do_hist = ghist != nullptr;
     if (do_hist) {
         for (int k = threadIdx.x; k < passes * 256; k += DUP_THREADS) sh[k] = 0;
         __syncthreads();
     }
-    const int depth_only = depth_bits / 8;  // passes whose 8-bit digit lies entirely in the depth bits
-    const int64_t i = (int64_t)blockIdx.x * DUP_THREADS + threadIdx.x;
+    // passes whose 8-bit digit lies entirely in the depth bits (none when the instance sort starts at the tile bits)
+    const int depth_only = depth_bits > bit_lo ? (depth_bits - bit_lo) / 8 : 0;
+    const int64_t j = (int64_t)blockIdx.x * DUP_THREADS + threadIdx.x;  // emission slot
     const int lane = threadIdx.x & 31;
     int32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     uint32_t dbits = 0;
-    int64_t off = 0;
+    int64_t off = 0, i = j;
     int cnt = 0;
-    if (i < n) {
+    if (j < n) {
+        if (perm) i = (int64_t)perm[j];  // emission order = depth order
         const int32_t r = radii[i];
         if (r > 0) {
             const float2 m = means2d[i];
             get_rect(m.x, m.y, r, grid_x, grid_y, x0, y0, x1, y1);
             dbits = __float_as_uint(depths[i]);
-            off = (i == 0) ? 0 : (int64_t)offsets[i - 1];
+            off = (j == 0) ? 0 : (int64_t)offsets[j - 1];
             cnt = (x1 - x0) * (y1 - y0);
         }
     }
@@ -172,7 +189,7 @@ duplicate_kernel(const int64_t n, const int32_t grid_x, const int32_t grid_y, co
     const uint32_t dlow = dbits - depth_base;
     const int first_pass = depth_only < passes ? depth_only : passes;
     if (do_hist && cnt > 0)
-        for (int p = 0; p < first_pass; p++) atomicAdd(&sh[p * 256 + ((dlow >> (8 * p)) & 255u)], (uint32_t)cnt);
+        for (int p = 0; p < first_pass; p++) atomicAdd(&sh[p * 256 + ((dlow >> (bit_lo + 8 * p)) & 255u)], (uint32_t)cnt);
     if (cnt > 0 && cnt <= DUP_SERIAL_MAX) {
         int64_t o = off;
         for (int32_t y = y0; y < y1; y++)
@@ -180,7 +197,7 @@ duplicate_kernel(const int64_t n, const int32_t grid_x, const int32_t grid_y, co
                 const uint64_t tile = (uint64_t)y * (uint64_t)grid_x + (uint64_t)x;
                 keys[o] = (tile << 32) | dbits;
                 vals[o] = id;
-                if (do_hist) hist_add_instance(sh, (tile << depth_bits) | dlow, first_pass, passes);
+                if (do_hist) hist_add_instance(sh, (tile << depth_bits) | dlow, first_pass, passes, bit_lo);
                 o++;
             }
     }
@@ -210,7 +227,7 @@ duplicate_kernel(const int64_t n, const int32_t grid_x, const int32_t grid_y, co
             if (do_hist) {  // neighbouring tiles share their high digits: aggregate within the warp
                 const uint64_t ck = (tile << depth_bits) | bdlow;
                 for (int p = first_pass; p < passes; p++) {
-                    const uint32_t d = valid ? (uint32_t)((ck >> (8 * p)) & 255u) : 0xffffffffu;
+                    const uint32_t d = valid ? (uint32_t)((ck >> (bit_lo + 8 * p)) & 255u) : 0xffffffffu;
                     const unsigned peers = __match_any_sync(0xffffffffu, d);
                     if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p * 256 + d], (uint32_t)__popc(peers));
                 }
@@ -225,6 +242,33 @@ duplicate_kernel(const int64_t n, const int32_t grid_x, const int32_t grid_y, co
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// depth pre-sort keys: canonical (flag << 32 | bits(depth)) with flag = 1 for culled Gaussians (they sort behind every
+// visible one and emit nothing); value = the 0-based Gaussian index
+// ----------------------------------------------------------------------------------------------------------
+// The digit histograms of the Gaussians' sort are accumulated here as well: depth digits are close to uniformly
+// random, so plain shared-memory atomics see few conflicts (MATCH.ANY aggregation, which pays off on clustered tile
+// digits, is at its slowest on such data).
+__global__ void __launch_bounds__(256)
+presort_keys_kernel(const int64_t n, const int32_t *__restrict__ radii, const float *__restrict__ depths,
+                    const int depth_bits, const uint32_t depth_base, const int passes, uint64_t *__restrict__ keys,
+                    uint32_t *__restrict__ vals, uint32_t *__restrict__ ghist /* [passes][256] */) {
+    __shared__ uint32_t sh[SORT_MAX_PASSES * 256];
+    for (int k = threadIdx.x; k < passes * 256; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool vis = radii[i] > 0;
+        const uint32_t dbits = vis ? __float_as_uint(depths[i]) : depth_base;
+        keys[i] = ((uint64_t)(vis ? 0u : 1u) << 32) | dbits;
+        vals[i] = (uint32_t)i;
+        const uint64_t ck = ((uint64_t)(vis ? 0u : 1u) << depth_bits) | (uint64_t)(dbits - depth_base);
+        for (int p = 0; p < passes; p++) atomicAdd(&sh[p * 256 + (uint32_t)((ck >> (8 * p)) & 255u)], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < passes * 256; k += blockDim.x)
+        if (sh[k]) atomicAdd(&ghist[k], sh[k]);
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // onesweep radix sort on the compact key  ck = (tile << depth_bits) | (bits(depth) - depth_base)
 // ----------------------------------------------------------------------------------------------------------
 constexpr int SORT_THREADS = 256;
@@ -232,6 +276,10 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 // keys per thread (template parameter of the pass kernel): 8 -> 2048-key tiles, ~50 registers, 34 KB smem
 // (5 CTAs/SM); 16 -> 4096-key tiles, 80 registers, 59 KB (3 CTAs/SM).  The pass is latency-bound, so occupancy wins.
 constexpr uint32_t ST_AGG = 1u << 30, ST_INC = 2u << 30, ST_MASK = (1u << 30) - 1;
+#ifndef GSR_SORT_LOOKBACK
+#define GSR_SORT_LOOKBACK 4
+#endif
+constexpr int LOOKBACK = GSR_SORT_LOOKBACK;  // status words of that many preceding tiles fetched per round trip
 
 __device__ __forceinline__ uint64_t compact_key(uint64_t key, int depth_bits, uint32_t depth_base) {
     const uint32_t lo = (uint32_t)key - depth_base;
@@ -240,7 +288,7 @@ __device__ __forceinline__ uint64_t compact_key(uint64_t key, int depth_bits, ui
 
 __global__ void __launch_bounds__(256)
 hist_kernel(const uint64_t *__restrict__ keys, const int64_t m, const int depth_bits, const uint32_t depth_base,
-            const int passes, uint32_t *__restrict__ ghist /* [passes][256] */) {
+            const int bit_lo, const int passes, uint32_t *__restrict__ ghist /* [passes][256] */) {
     __shared__ uint32_t sh[SORT_MAX_PASSES * 256];
     const int lane = threadIdx.x & 31;
     for (int k = threadIdx.x; k < passes * 256; k += blockDim.x) sh[k] = 0;
@@ -265,7 +313,7 @@ hist_kernel(const uint64_t *__restrict__ keys, const int64_t m, const int depth_
             const bool valid = i0 + u < m;
             const uint64_t ck = compact_key(k4[u], depth_bits, depth_base);
             for (int p = 0; p < passes; p++) {
-                const uint32_t d = valid ? (uint32_t)((ck >> (8 * p)) & 255u) : 0xffffffffu;
+                const uint32_t d = valid ? (uint32_t)((ck >> (bit_lo + 8 * p)) & 255u) : 0xffffffffu;
                 const unsigned peers = __match_any_sync(0xffffffffu, d);  // warp-aggregated: tile digits cluster
                 if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p * 256 + d], (uint32_t)__popc(peers));
             }
@@ -394,16 +442,16 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
     }
 
     // ---- chained look-back over the preceding tiles, per digit; done AFTER the local scatter so that the
-    //      predecessors have had time to publish (4 predecessors per round trip, independent loads in flight)
+    //      predecessors have had time to publish (LOOKBACK predecessors per round trip, independent loads in flight)
     uint32_t tiles_prefix = 0;
     if (tile > 0) {
         bool found = false;
-        for (int64_t t = tile - 1; t >= 0 && !found; t -= 4) {
-            uint32_t sv[4];
+        for (int64_t t = tile - 1; t >= 0 && !found; t -= LOOKBACK) {
+            uint32_t sv[LOOKBACK];
 #pragma unroll
-            for (int j = 0; j < 4; j++) sv[j] = (t - j >= 0) ? ld_volatile_u32(status + (t - j) * 256 + tid) : ST_INC;
+            for (int j = 0; j < LOOKBACK; j++) sv[j] = (t - j >= 0) ? ld_volatile_u32(status + (t - j) * 256 + tid) : ST_INC;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < LOOKBACK; j++) {
                 if (found) break;
                 uint32_t sj = sv[j];
                 while ((sj >> 30) == 0) sj = ld_volatile_u32(status + (t - j) * 256 + tid);
@@ -473,24 +521,53 @@ size_t scan_state_words(int64_t n) {  // in 64-bit words
     return 1 + (size_t)((n + SCAN_TILE - 1) / SCAN_TILE);
 }
 
-void launch_scan_tiles(int64_t n, const int32_t *tiles_touched, int32_t *points_offset, uint32_t *scan_state,
-                       int64_t *total_dev, cudaStream_t s) {
+void launch_scan_tiles(int64_t n, const int32_t *tiles_touched, const uint32_t *perm, int32_t *offsets,
+                       uint32_t *scan_state, int64_t *total_dev, cudaStream_t s) {
     if (n <= 0) return;
     const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     cudaMemsetAsync(scan_state, 0, scan_state_words(n) * sizeof(unsigned long long), s);
-    scan_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(n, tiles_touched, points_offset,
+    scan_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(n, tiles_touched, perm, offsets,
                                                         reinterpret_cast<unsigned long long *>(scan_state), total_dev);
     count_launch();
 }
 
-void launch_duplicate(const DevCamera &cam, int64_t n, const GeomPtrs &g, uint64_t *keys, uint32_t *vals,
-                      const SortPlan &plan, uint32_t *ghist, cudaStream_t s) {
+void launch_duplicate(const DevCamera &cam, int64_t n, const GeomPtrs &g, const int32_t *offsets, const uint32_t *perm,
+                      uint64_t *keys, uint32_t *vals, const SortPlan &plan, uint32_t *ghist, cudaStream_t s) {
     if (n <= 0) return;
     const int64_t blocks = (n + DUP_THREADS - 1) / DUP_THREADS;
     duplicate_kernel<<<(unsigned)blocks, DUP_THREADS, 0, s>>>(n, cam.grid_x, cam.grid_y, g.radii, g.means2d, g.depths,
-                                                             g.points_offset, keys, vals, plan.depth_bits,
-                                                             plan.depth_base, plan.passes, ghist);
+                                                             offsets, perm, keys, vals, plan.depth_bits, plan.depth_base,
+                                                             plan.bit_lo, plan.passes, ghist);
     count_launch();
+}
+
+// plan = presort_plan(...); ghist = sort_prepare(plan, ...): the histograms are ready for launch_sort_pairs afterwards
+void launch_presort_keys(int64_t n, const GeomPtrs &g, const SortPlan &plan, uint64_t *keys, uint32_t *vals,
+                         uint32_t *ghist, cudaStream_t s) {
+    if (n <= 0) return;
+    int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);  // ~8 Gaussians per thread: few histogram flushes
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    presort_keys_kernel<<<(unsigned)blocks, 256, 0, s>>>(n, g.radii, g.depths, plan.depth_bits, plan.depth_base,
+                                                         plan.passes, keys, vals, ghist);
+    count_launch();
+}
+
+// the Gaussians' own sort: flag bit + depth bits
+SortPlan presort_plan(const SortPlan &plan) {
+    SortPlan p = plan;
+    p.tile_bits = 1;
+    p.bit_lo = 0;
+    p.small = 1;
+    p.passes = (p.tile_bits + p.depth_bits + 7) / 8;
+    return p;
+}
+
+// the instance sort after a depth pre-sort: tile digits only
+SortPlan tile_only_plan(const SortPlan &plan) {
+    SortPlan p = plan;
+    p.bit_lo = plan.depth_bits;
+    p.passes = (p.tile_bits + 7) / 8;
+    return p;
 }
 
 SortPlan make_sort_plan(int64_t n_tiles, float near_plane, float far_plane) {
@@ -507,22 +584,28 @@ SortPlan make_sort_plan(int64_t n_tiles, float near_plane, float far_plane) {
         p.depth_bits = 32;
     }
     if (p.depth_bits < 1) p.depth_bits = 1;
+    p.bit_lo = 0;
+    p.small = 0;
     p.passes = (p.tile_bits + p.depth_bits + 7) / 8;
     return p;
 }
 
-int sort_ipt() {
-    static int v = -1;
+// keys per thread of the pass kernel: 16 for the instance sort; the Gaussians' sort (plan.small) is a single partial
+// wave either way, so it takes the 2048-key tiles whose per-CTA latency is half
+int sort_ipt(const SortPlan &plan) {
+    static int v = -1, vs = -1;
     if (v < 0) {
         const char *e = getenv("GSR_SORT_IPT");
         v = (e && atoi(e) == 8) ? 8 : 16;
+        const char *es = getenv("GSR_PRESORT_IPT");
+        vs = (es && atoi(es) == 16) ? 16 : 8;
     }
-    return v;
+    return plan.small ? vs : v;
 }
-static int64_t sort_tile_keys() { return (int64_t)SORT_THREADS * sort_ipt(); }
+static int64_t sort_tile_keys(const SortPlan &plan) { return (int64_t)SORT_THREADS * sort_ipt(plan); }
 
 size_t sort_temp_words(int64_t m, const SortPlan &plan) {  // in 32-bit words
-    const size_t tiles = (size_t)((m + sort_tile_keys() - 1) / sort_tile_keys());
+    const size_t tiles = (size_t)((m + sort_tile_keys(plan) - 1) / sort_tile_keys(plan));
     return (size_t)plan.passes * 256 /* ghist */ + (size_t)plan.passes * tiles * 256 /* status */ +
            SORT_MAX_PASSES /* tile counters */;
 }
@@ -545,15 +628,15 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
         cudaFuncSetAttribute(onesweep_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<16>));
         attr_set = true;
     }
-    const int ipt = sort_ipt();
-    const size_t tiles = (size_t)((m + sort_tile_keys() - 1) / sort_tile_keys());
+    const int ipt = sort_ipt(plan);
+    const size_t tiles = (size_t)((m + sort_tile_keys(plan) - 1) / sort_tile_keys(plan));
     uint32_t *ghist = temp_words;
     uint32_t *status = ghist + (size_t)plan.passes * 256;
     uint32_t *counters = status + (size_t)plan.passes * tiles * 256;
     if (!hist_ready) {
         int hb = (int)((m + 256 * 16 - 1) / (256 * 16));
         if (hb > 148 * 8) hb = 148 * 8;
-        hist_kernel<<<hb, 256, 0, s>>>(keys_in, m, plan.depth_bits, plan.depth_base, plan.passes, ghist);
+        hist_kernel<<<hb, 256, 0, s>>>(keys_in, m, plan.depth_bits, plan.depth_base, plan.bit_lo, plan.passes, ghist);
         count_launch();
     }
     const uint64_t *ksrc = keys_in;
@@ -565,8 +648,9 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
     }
     const int total_bits = plan.tile_bits + plan.depth_bits;
     for (int p = 0; p < plan.passes; p++) {
-        const int digit_bits = total_bits - 8 * p < 8 ? total_bits - 8 * p : 8;
-        const bool has_tile_bits = 8 * p + 8 > plan.depth_bits;
+        const int shift = plan.bit_lo + 8 * p;
+        const int digit_bits = total_bits - shift < 8 ? total_bits - shift : 8;
+        const bool has_tile_bits = shift + 8 > plan.depth_bits;
         const int ballot_bits = (rank_mode == 1 || (rank_mode == 2 && has_tile_bits)) ? digit_bits : 0;
         // the chain must end in (keys_out, vals_out) and never write the input
         const bool to_out = ((plan.passes - 1 - p) % 2) == 0;
@@ -574,7 +658,7 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
         uint32_t *vdst = to_out ? vals_out : vals_tmp;
 #define GSR_ONESWEEP(IPT, BAL)                                                                                       \
     onesweep_kernel<IPT, BAL><<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem<IPT>), s>>>(                              \
-        ksrc, vsrc, kdst, vdst, m, 8 * p, plan.depth_bits, plan.depth_base, ghist + (size_t)p * 256,                    \
+        ksrc, vsrc, kdst, vdst, m, shift, plan.depth_bits, plan.depth_base, ghist + (size_t)p * 256,                    \
         status + (size_t)p * tiles * 256, counters + p, ballot_bits)
         if (ipt == 16) {
             if (ballot_bits) GSR_ONESWEEP(16, true); else GSR_ONESWEEP(16, false);

@@ -64,17 +64,25 @@ void launch_preprocess(const DevCamera &cam, int64_t n, int sh_degree, int K, in
                        const float *shs, const float *opac, const float *scales, const float *rots,
                        const GeomPtrs &g, cudaStream_t s, const ParamSpec &ps = ParamSpec());
 
-void launch_scan_tiles(int64_t n, const int32_t *tiles_touched, int32_t *points_offset, uint32_t *scan_state,
-                       int64_t *total_dev, cudaStream_t s);
+// perm != nullptr: scan of tiles_touched[perm[j]] (emission in depth order)
+void launch_scan_tiles(int64_t n, const int32_t *tiles_touched, const uint32_t *perm, int32_t *offsets,
+                       uint32_t *scan_state, int64_t *total_dev, cudaStream_t s);
 size_t scan_state_words(int64_t n);
 
 struct SortPlan {
     int tile_bits, depth_bits, passes;
     uint32_t depth_base;
+    int bit_lo;  // first bit of the compact key (tile << depth_bits | depth - depth_base) the passes sort on
+    int small;   // 1: a sort over the N Gaussians (latency-bound partial wave): smaller pass tiles
 };
+SortPlan presort_plan(const SortPlan &plan);    // the Gaussians' own depth sort (flag bit + depth bits)
+SortPlan tile_only_plan(const SortPlan &plan);  // the instance sort once emission is in depth order
+void launch_presort_keys(int64_t n, const GeomPtrs &g, const SortPlan &plan, uint64_t *keys, uint32_t *vals, uint32_t *ghist,
+                         cudaStream_t s);
 // ghist != nullptr: also accumulate the radix-sort digit histograms [passes][256] (zeroed by sort_prepare)
-void launch_duplicate(const DevCamera &cam, int64_t n, const GeomPtrs &g, uint64_t *keys, uint32_t *vals,
-                      const SortPlan &plan, uint32_t *ghist, cudaStream_t s);
+// offsets: inclusive scan of tiles touched in EMISSION order; perm != nullptr: emission slot j is Gaussian perm[j]
+void launch_duplicate(const DevCamera &cam, int64_t n, const GeomPtrs &g, const int32_t *offsets, const uint32_t *perm,
+                      uint64_t *keys, uint32_t *vals, const SortPlan &plan, uint32_t *ghist, cudaStream_t s);
 SortPlan make_sort_plan(int64_t n_tiles, float near_plane, float far_plane);
 size_t sort_temp_words(int64_t m, const SortPlan &plan);
 // keys_in/vals_in are left intact; result lands in keys_out/vals_out; (keys_tmp, vals_tmp) is scratch of size m.

@@ -18,7 +18,8 @@ namespace {
 std::atomic<int64_t> g_launches{0};
 const char *const kStageNames[GSR_NUM_STAGES] = {"gsr:preprocess", "gsr:scan",       "gsr:duplicate",
                                                  "gsr:sort",       "gsr:ranges",     "gsr:render_fwd",
-                                                 "gsr:zero_grads", "gsr:render_bwd", "gsr:gauss_bwd"};
+                                                 "gsr:zero_grads", "gsr:render_bwd", "gsr:gauss_bwd",
+                                                 "gsr:presort"};
 thread_local std::string g_create_error;
 
 struct DevBuf {
@@ -52,6 +53,17 @@ struct GsrHandle {
     // ImageState
     uint32_t *ranges = nullptr, *n_contrib = nullptr;
     float *accum_alpha = nullptr;
+    // depth pre-sort of the Gaussians (binning.cu): ping-pong pairs, the permutation, tiles touched scanned in that order
+    bool presort = true;               // GSR_PRESORT=0 restores the single 5-pass instance sort (A/B measurements)
+    SortPlan pplan, tplan;             // the Gaussians' sort / the tile-digit instance sort that follows it
+    uint64_t *pk[3] = {nullptr, nullptr, nullptr};
+    uint32_t *pv[3] = {nullptr, nullptr, nullptr};
+    uint32_t *psort_temp = nullptr;
+    size_t psort_temp_cap = 0;
+    int32_t *offsets_sorted = nullptr;
+    bool ref_binning_valid = false;    // points_offset / keys_unsorted / values_unsorted hold the reference's content
+    cudaStream_t last_stream = nullptr;
+    DevCamera last_cam{};
     // scan
     uint32_t *scan_state = nullptr;
     size_t scan_cap = 0;  // 64-bit words
@@ -137,6 +149,13 @@ void free_geometry(GsrHandle *h) {
     else dev_free(h, h->g.gacc, (size_t)acc_floats(ch) * n);
     dev_free(h, h->scan_state, 2 * h->scan_cap);
     h->scan_cap = 0;
+    for (int k = 0; k < 3; k++) {
+        dev_free(h, h->pk[k], n);
+        dev_free(h, h->pv[k], n);
+    }
+    dev_free(h, h->psort_temp, h->psort_temp_cap);
+    h->psort_temp_cap = 0;
+    dev_free(h, h->offsets_sorted, n);
     h->cap_n = 0;
 }
 
@@ -180,6 +199,15 @@ int ensure_geometry_alloc(GsrHandle *h, int64_t n, cudaStream_t s) {
     }
     h->scan_cap = scan_state_words(n);
     CK(dev_alloc(h, &h->scan_state, 2 * h->scan_cap));
+    if (h->presort) {
+        for (int k = 0; k < 3; k++) {
+            CK(dev_alloc(h, &h->pk[k], c));
+            CK(dev_alloc(h, &h->pv[k], c));
+        }
+        h->psort_temp_cap = sort_temp_words(n, h->pplan);
+        CK(dev_alloc(h, &h->psort_temp, h->psort_temp_cap));
+        CK(dev_alloc(h, &h->offsets_sorted, c));
+    }
     // KA.zeros in the reference (states.jl:30-47): stale-state reads of never-visible rows see zeros.  Enqueued on
     // the caller's stream: a legacy-stream cudaMemset is not ordered against a cudaStreamNonBlocking stream (torch
     // side streams) and could land after this forward's preprocess kernel.
@@ -302,6 +330,12 @@ int gsr_create(const GsrConfig *cfg, GsrHandle **out) {
     h->grid_y = cfg->height / GSR_TILE;
     h->n_tiles = (int64_t)h->grid_x * h->grid_y;
     h->plan = make_sort_plan(h->n_tiles, cfg->near_plane, cfg->far_plane);
+    h->pplan = presort_plan(h->plan);
+    h->tplan = tile_only_plan(h->plan);
+    {
+        const char *e = getenv("GSR_PRESORT");
+        h->presort = !(e && atoi(e) == 0);
+    }
     const size_t px = (size_t)cfg->width * cfg->height;
     int rc = GSR_OK;
     do {
@@ -371,9 +405,22 @@ int gsr_memory_usage(const GsrHandle *h, size_t *bytes) {
     return GSR_OK;
 }
 
-int gsr_get_state(const GsrHandle *h, GsrStateViews *v) {
+int gsr_get_state(GsrHandle *h, GsrStateViews *v) {
     if (!h || !v) return GSR_EINVAL;
     memset(v, 0, sizeof *v);
+    if (!h->ref_binning_valid && h->fwd_valid && h->last_n > 0) {
+        // With the depth pre-sort the hot path scans and emits in depth order; the reference's intermediate buffers —
+        // cumsum(tiles_touched) in index order (rasterizer.jl:333) and the unsorted keys / values of duplicate_with_keys!
+        // (utils.jl:85-120) — are reproduced here, on demand, for whoever reads the state.  The sort has consumed the
+        // depth-order emission by now, so its buffers are free to hold the reference-order one.
+        cudaStream_t s = h->last_stream;
+        launch_scan_tiles(h->last_n, h->g.tiles_touched, nullptr, h->g.points_offset, h->scan_state, h->total_dev, s);
+        if (h->last_m > 0)
+            launch_duplicate(h->last_cam, h->last_n, h->g, h->g.points_offset, nullptr, h->keys_unsorted, h->vals_unsorted,
+                             h->plan, nullptr, s);
+        CK(cudaStreamSynchronize(s));
+        h->ref_binning_valid = true;
+    }
     v->n = h->last_n;
     v->n_rendered = h->last_m;
     v->radii = h->g.radii;
@@ -428,13 +475,26 @@ static int forward_impl(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t s
             StageTimer tm(h, s, GSR_STAGE_PREPROCESS);
             launch_preprocess(dc, n, sh_degree, K, ch, means, shs, opacities, scales, rotations, h->g, s, ps);
         }
+        const uint32_t *perm = nullptr;
+        if (h->presort) {  // Gaussians in depth order: the instance sort below then only has the tile digits left
+            StageTimer tm(h, s, GSR_STAGE_PRESORT);
+            uint32_t *phist = sort_prepare(h->pplan, n, h->psort_temp, s);
+            launch_presort_keys(n, h->g, h->pplan, h->pk[0], h->pv[0], phist, s);
+            launch_sort_pairs(h->pplan, n, h->pk[0], h->pv[0], h->pk[1], h->pv[1], h->pk[2], h->pv[2], h->psort_temp,
+                              /*hist_ready=*/true, s);
+            perm = h->pv[1];
+        }
         {
             StageTimer tm(h, s, GSR_STAGE_SCAN);
-            launch_scan_tiles(n, h->g.tiles_touched, h->g.points_offset, h->scan_state, h->total_dev, s);
+            launch_scan_tiles(n, h->g.tiles_touched, perm, perm ? h->offsets_sorted : h->g.points_offset, h->scan_state,
+                              h->total_dev, s);
         }
         CK(cudaStreamSynchronize(s));  // the one host sync of the forward (rasterizer.jl:337)
         m = *h->total_host;
     }
+    h->ref_binning_valid = !h->presort;
+    h->last_stream = s;
+    h->last_cam = dc;
 
     h->last_n = n;
     h->last_m = m;
@@ -447,14 +507,16 @@ static int forward_impl(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t s
     rc = ensure_binning(h, m);
     if (rc) return rc;
 
+    const SortPlan &iplan = h->presort ? h->tplan : h->plan;  // instance sort: tile digits only after the pre-sort
     {
         StageTimer tm(h, s, GSR_STAGE_DUPLICATE);
-        uint32_t *ghist = sort_prepare(h->plan, m, h->sort_temp, s);
-        launch_duplicate(dc, n, h->g, h->keys_unsorted, h->vals_unsorted, h->plan, ghist, s);
+        uint32_t *ghist = sort_prepare(iplan, m, h->sort_temp, s);
+        launch_duplicate(dc, n, h->g, h->presort ? h->offsets_sorted : h->g.points_offset, h->presort ? h->pv[1] : nullptr,
+                         h->keys_unsorted, h->vals_unsorted, iplan, ghist, s);
     }
     {
         StageTimer tm(h, s, GSR_STAGE_SORT);
-        launch_sort_pairs(h->plan, m, h->keys_unsorted, h->vals_unsorted, h->keys_sorted, h->vals_sorted, h->keys_tmp,
+        launch_sort_pairs(iplan, m, h->keys_unsorted, h->vals_unsorted, h->keys_sorted, h->vals_sorted, h->keys_tmp,
                           h->vals_tmp, h->sort_temp, /*hist_ready=*/true, s);
     }
     {

@@ -43,7 +43,8 @@ EXPORTS = ["gsr_version", "gsr_last_error", "gsr_create", "gsr_destroy", "gsr_re
            "gsr_backward_gaussians_peers", "gsr_ssim_forward", "gsr_ssim_backward", "gsr_photometric_loss", "gsr_forward_raw", "gsr_backward_raw", "gsr_ply_open", "gsr_ply_read",
            "gsr_ply_close", "gsr_ply_write", "gsr_ply_write_scales", "gsr_ply_last_error", "gsr_densify_masks", "gsr_prune_mask",
            "gsr_mask_offsets_scratch_words", "gsr_mask_offsets", "gsr_gather_rows", "gsr_split_children"]
-STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "render_fwd", "zero_grads", "render_bwd", "gauss_bwd"]
+STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "render_fwd", "zero_grads", "render_bwd", "gauss_bwd",
+          "presort"]
 
 
 HASH_PATH = os.path.join(CSRC, "libgsrast.srchash")

@@ -121,7 +121,10 @@ GSR_API int gsr_destroy(GsrHandle *h);
 GSR_API int gsr_release_scene_buffers(GsrHandle *h);
 /* memory_usage(rast) — rasterizer.jl:127-134 (workspace bytes owned by the handle) */
 GSR_API int gsr_memory_usage(const GsrHandle *h, size_t *bytes);
-GSR_API int gsr_get_state(const GsrHandle *h, GsrStateViews *views);
+/* Views of the state of the last forward.  points_offset / keys_unsorted / values_unsorted — intermediates the hot path
+ * does not need in the reference's layout (it scans and emits in depth order) — are written, in the reference's order,
+ * by this call when they are first asked for (two launches + a stream synchronisation on the forward's stream). */
+GSR_API int gsr_get_state(GsrHandle *h, GsrStateViews *views);
 /* Number of forwards this handle has run.  gsr_backward differentiates the LAST forward (its per-pixel and binning
  * state live in the handle, as rast.{g,b,i}state do in the reference): a caller that interleaves forwards keeps the
  * value returned after its forward and compares before its backward (the Python mirror and the Julia shim raise). */
@@ -318,6 +321,7 @@ enum {
     GSR_STAGE_ZERO_GRADS,     /* zero-fill of the per-Gaussian accumulators */
     GSR_STAGE_RENDER_BWD,     /* ∇render! */
     GSR_STAGE_GAUSS_BWD,      /* ∇project! + ∇spherical_harmonics! */
+    GSR_STAGE_PRESORT,        /* depth sort of the Gaussians ahead of cumsum! / duplicate_with_keys! (part of the sort) */
     GSR_NUM_STAGES
 };
 GSR_API int gsr_profile_enable(GsrHandle *h, int32_t enable);
