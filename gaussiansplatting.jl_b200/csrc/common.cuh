@@ -118,17 +118,18 @@ void launch_update_stats(int64_t n, const int32_t *radii, const float2 *grad_mea
 int launch_fp32_peak(cudaStream_t s, double *ms, double *flops);
 
 // ---- peer-fused per-Gaussian backward (backward_peers.cu) --------------------------------------------------
-#define GSR_MAX_PEERS 8
+#define GSR_MAX_PEERS 8    // ranks of one node
+#define GSR_MAX_VIEWS 16   // views of one batch summed by gsr_backward_gaussians_views
 struct PeerCamera {
     float R[9], t[3], focal[2], principal[2], cam_center[3];
     int32_t width, height;
     float blur_eps;
 };
 struct PeerArgs {
-    PeerCamera cams[GSR_MAX_PEERS];
-    const float *gacc[GSR_MAX_PEERS];  // peer accumulators [n][AF]
-    float *table[GSR_MAX_PEERS];       // peer gradient tables: [vrot 4n | vmeans 3n | vscales 3n | vopac n | vshs 3Kn]
-    int32_t world, rank;
+    PeerCamera cams[GSR_MAX_VIEWS];    // one camera per view of the batch
+    const float *gacc[GSR_MAX_VIEWS];  // that view's accumulator [n][AF], in the memory of the rank that rendered it
+    float *table[GSR_MAX_PEERS];       // every rank's gradient table: [vrot 4n | vmeans 3n | vscales 3n | vopac n | vshs 3Kn]
+    int32_t n_views, world, rank;
     int64_t n, lo, hi;
     int32_t sh_degree, K, channels, sh_stride;
     int32_t vsh_aligned;  // every table's SH segment (offset 11n floats) is 16-byte aligned

@@ -639,8 +639,17 @@ int gsr_set_accumulator(GsrHandle *h, float *gacc_dev, int64_t capacity_gaussian
     if (!h) return GSR_EINVAL;
     if ((gacc_dev == nullptr) != (capacity_gaussians == 0) || (reinterpret_cast<uintptr_t>(gacc_dev) & 15))
         return fail(h, GSR_EINVAL, "gsr_set_accumulator: need a 16-byte aligned buffer and its capacity (or NULL, 0)");
-    free_geometry(h);  // the geometry state is rebuilt around the new accumulator on the next forward
-    h->fwd_valid = false;
+    if (gacc_dev == h->gacc_external && capacity_gaussians == h->gacc_external_cap) return GSR_OK;
+    const size_t af = (size_t)acc_floats(h->cfg.channels);
+    if (h->cap_n > 0 && gacc_dev && capacity_gaussians >= h->cap_n) {
+        // Only the pointer changes (one accumulator per view of a batch): the forward never touches the accumulator, so
+        // the state of the last forward stays valid and nothing else is reallocated.
+        if (!h->gacc_external) dev_free(h, h->g.gacc, af * (size_t)h->cap_n);  // the private buffer is no longer needed
+        h->g.gacc = gacc_dev;
+    } else {
+        free_geometry(h);  // the geometry state is rebuilt around the new accumulator on the next forward
+        h->fwd_valid = false;
+    }
     h->gacc_external = gacc_dev;
     h->gacc_external_cap = capacity_gaussians;
     return GSR_OK;
@@ -670,25 +679,27 @@ int gsr_backward_render(GsrHandle *h, int64_t n, const float background[3], cons
     return GSR_OK;
 }
 
-int gsr_backward_gaussians_peers(GsrHandle *h, int32_t world, int32_t rank, const GsrCamera *cams,
-                                 const float *const *peer_gacc, float *const *peer_tables, int64_t n, int32_t sh_degree,
+int gsr_backward_gaussians_views(GsrHandle *h, int32_t n_views, const GsrCamera *cams, const float *const *view_gacc,
+                                 int32_t world, int32_t rank, float *const *peer_tables, int64_t n, int32_t sh_degree,
                                  int32_t K, const float *means, const float *shs, const float *opacities,
                                  const float *scales, const float *rotations, void *stream) {
     if (!h) return GSR_EINVAL;
-    if (world < 1 || world > GSR_MAX_PEERS || rank < 0 || rank >= world || !cams || !peer_gacc || !peer_tables)
-        return fail(h, GSR_EINVAL, "gsr_backward_gaussians_peers: need 1 <= world <= 8 and per-rank camera / pointer arrays");
+    if (n_views < 1 || n_views > GSR_MAX_VIEWS || !cams || !view_gacc)
+        return fail(h, GSR_EINVAL, "gsr_backward_gaussians_views: need 1 <= n_views <= 16 and per-view camera / accumulator arrays");
+    if (world < 1 || world > GSR_MAX_PEERS || rank < 0 || rank >= world || !peer_tables)
+        return fail(h, GSR_EINVAL, "gsr_backward_gaussians_views: need 1 <= world <= 8, 0 <= rank < world and per-rank tables");
     if (!means || !shs || !opacities || !scales || !rotations || n < 0)
-        return fail(h, GSR_EINVAL, "gsr_backward_gaussians_peers: null parameter array");
+        return fail(h, GSR_EINVAL, "gsr_backward_gaussians_views: null parameter array");
     if (sh_degree < 0 || sh_degree > 3 || K < (sh_degree + 1) * (sh_degree + 1))
-        return fail(h, GSR_EINVAL, "gsr_backward_gaussians_peers: need 0 <= sh_degree <= 3 and K >= (sh_degree+1)^2");
+        return fail(h, GSR_EINVAL, "gsr_backward_gaussians_views: need 0 <= sh_degree <= 3 and K >= (sh_degree+1)^2");
     if (n == 0) return GSR_OK;
     PeerArgs a;
     memset(&a, 0, sizeof a);
     a.vsh_aligned = 1;
-    for (int v = 0; v < world; v++) {
-        if (!peer_gacc[v] || !peer_tables[v]) return fail(h, GSR_EINVAL, "gsr_backward_gaussians_peers: null peer pointer");
-        if ((reinterpret_cast<uintptr_t>(peer_gacc[v]) & 15) || (reinterpret_cast<uintptr_t>(peer_tables[v]) & 15))
-            return fail(h, GSR_EINVAL, "gsr_backward_gaussians_peers: peer buffers must be 16-byte aligned");
+    for (int v = 0; v < n_views; v++) {
+        if (!view_gacc[v]) return fail(h, GSR_EINVAL, "gsr_backward_gaussians_views: null accumulator pointer");
+        if (reinterpret_cast<uintptr_t>(view_gacc[v]) & 15)
+            return fail(h, GSR_EINVAL, "gsr_backward_gaussians_views: accumulators must be 16-byte aligned");
         memcpy(a.cams[v].R, cams[v].R, sizeof a.cams[v].R);
         memcpy(a.cams[v].t, cams[v].t, sizeof a.cams[v].t);
         memcpy(a.cams[v].focal, cams[v].focal, sizeof a.cams[v].focal);
@@ -697,10 +708,16 @@ int gsr_backward_gaussians_peers(GsrHandle *h, int32_t world, int32_t rank, cons
         a.cams[v].width = h->cfg.width;
         a.cams[v].height = h->cfg.height;
         a.cams[v].blur_eps = h->cfg.blur_eps;
-        a.gacc[v] = peer_gacc[v];
-        a.table[v] = peer_tables[v];
-        if (reinterpret_cast<uintptr_t>(peer_tables[v] + 11 * n) & 15) a.vsh_aligned = 0;
+        a.gacc[v] = view_gacc[v];
     }
+    for (int p = 0; p < world; p++) {
+        if (!peer_tables[p]) return fail(h, GSR_EINVAL, "gsr_backward_gaussians_views: null table pointer");
+        if (reinterpret_cast<uintptr_t>(peer_tables[p]) & 15)
+            return fail(h, GSR_EINVAL, "gsr_backward_gaussians_views: tables must be 16-byte aligned");
+        a.table[p] = peer_tables[p];
+        if (reinterpret_cast<uintptr_t>(peer_tables[p] + 11 * n) & 15) a.vsh_aligned = 0;
+    }
+    a.n_views = n_views;
     a.world = world;
     a.rank = rank;
     a.n = n;
@@ -715,8 +732,17 @@ int gsr_backward_gaussians_peers(GsrHandle *h, int32_t world, int32_t rank, cons
     a.means = means; a.shs = shs; a.opac = opacities; a.scales = scales; a.rots = rotations;
     StageTimer tm(h, static_cast<cudaStream_t>(stream), GSR_STAGE_GAUSS_BWD);
     if (launch_backward_gaussians_peers(a, static_cast<cudaStream_t>(stream)) != 0)
-        return fail(h, GSR_ECUDA, "gsr_backward_gaussians_peers: launch failed");
+        return fail(h, GSR_ECUDA, "gsr_backward_gaussians_views: launch failed");
     return GSR_OK;
+}
+
+int gsr_backward_gaussians_peers(GsrHandle *h, int32_t world, int32_t rank, const GsrCamera *cams,
+                                 const float *const *peer_gacc, float *const *peer_tables, int64_t n, int32_t sh_degree,
+                                 int32_t K, const float *means, const float *shs, const float *opacities,
+                                 const float *scales, const float *rotations, void *stream) {
+    // one view per rank: view v's accumulator is rank v's
+    return gsr_backward_gaussians_views(h, world, cams, peer_gacc, world, rank, peer_tables, n, sh_degree, K, means, shs,
+                                        opacities, scales, rotations, stream);
 }
 
 int gsr_update_stats(GsrHandle *h, int64_t n, int32_t *max_radii, float *accum_grad_means2d, float *denom,

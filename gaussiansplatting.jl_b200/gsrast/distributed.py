@@ -82,46 +82,84 @@ def render_view_batch(rast, params: dict, cameras: list, vpixels: list, table: G
     return mine
 
 
-class PeerFusedBackward:
-    """Per-Gaussian backward fused with the cross-GPU gradient reduction over NVLink peer memory
-    (csrc/backward_peers.cu): replaces `backward_gaussians + all_reduce(table)`.
+def view_owner(view: int, world: int) -> tuple[int, int]:
+    """(rank that renders `view`, its index among that rank's views) under round-robin sharding."""
+    return view % world, view // world
 
-    Every rank keeps its moment accumulator (48/64 B per Gaussian) and its gradient table in symmetric memory
-    (torch.distributed._symmetric_memory).  After the local compositing backward, rank r loads all ranks' accumulator
-    rows for ITS slice of Gaussians over NVLink, applies each view's ∇project / ∇SH chain, sums, and stores the
-    reduced rows into every rank's table.  Result == the all-reduced table (same layout as `GradientTable`)."""
+
+class ViewBatchBackward:
+    """A batch of V views (V <= 16) sharded round-robin over the ranks — several views per rank, or all of them on one
+    GPU — with ONE fused per-Gaussian backward + exchange per batch (csrc/backward_peers.cu, gsr_backward_gaussians_views).
+
+    Every view gets its own moment accumulator (48/64 B per Gaussian).  After this rank's forwards and compositing
+    backwards, rank r reduces ITS slice of the Gaussians over all V accumulators — loading the other ranks' rows over
+    NVLink — and stores the finished rows into every rank's table: compute + reduce-scatter + all-gather in one kernel,
+    once per batch.  On a single GPU (world == 1, no process group needed) the same kernel replaces V accumulating
+    `gsr_backward` calls: the parameters are read once and the gradient table is written once instead of V
+    read-modify-write passes.  Result == sum over the V views of ∇rasterize, same layout as `GradientTable`."""
 
     def __init__(self, rast, n: int, K: int, cameras: list, group=None):
-        import torch.distributed._symmetric_memory as symm_mem
-        self.group = group if group is not None else dist.group.WORLD
-        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        assert len(cameras) == self.world, "one camera (view) per rank"
-        self.rast, self.n, self.K, self.cameras = rast, n, K, cameras
-        af = 12 if rast.channels <= 6 else 16
+        self.rast, self.n, self.K, self.cameras = rast, n, K, list(cameras)
+        self.V = len(self.cameras)
+        assert 1 <= self.V <= 16, "1..16 views per batch"
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.group = (group if group is not None else dist.group.WORLD) if multi else None
+        self.world = dist.get_world_size(self.group) if multi else 1
+        self.rank = dist.get_rank(self.group) if multi else 0
+        self.mine = views_for_rank(self.V, self.rank, self.world)
+        self.af = 12 if rast.channels <= 6 else 16
         dev = rast.device
-        self.gacc = symm_mem.empty(n * af, dtype=torch.float32, device=dev)
-        self.h_gacc = symm_mem.rendezvous(self.gacc, self.group)
+        slots = (self.V + self.world - 1) // self.world  # accumulators per rank (same on every rank: symmetric)
         per = 4 + 3 + 3 + 1 + 3 * K
-        self.table_flat = symm_mem.empty(n * per, dtype=torch.float32, device=dev)
-        self.h_table = symm_mem.rendezvous(self.table_flat, self.group)
-        self.gacc_ptrs = list(self.h_gacc.buffer_ptrs)
-        self.table_ptrs = list(self.h_table.buffer_ptrs)
-        rast.set_accumulator(self.gacc)
+        if multi:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.gacc = symm_mem.empty(slots * n * self.af, dtype=torch.float32, device=dev)
+            self.h_gacc = symm_mem.rendezvous(self.gacc, self.group)
+            self.table_flat = symm_mem.empty(n * per, dtype=torch.float32, device=dev)
+            self.h_table = symm_mem.rendezvous(self.table_flat, self.group)
+            bases, self.table_ptrs = list(self.h_gacc.buffer_ptrs), list(self.h_table.buffer_ptrs)
+        else:
+            self.gacc = torch.empty(slots * n * self.af, dtype=torch.float32, device=dev)
+            self.table_flat = torch.empty(n * per, dtype=torch.float32, device=dev)
+            self.h_gacc = self.h_table = None
+            bases, self.table_ptrs = [self.gacc.data_ptr()], [self.table_flat.data_ptr()]
+        stride = n * self.af * 4
+        self.view_ptrs = [bases[view_owner(v, self.world)[0]] + view_owner(v, self.world)[1] * stride for v in range(self.V)]
+        self.local_acc = [self.gacc[j * n * self.af:(j + 1) * n * self.af] for j in range(slots)]
         self.views, off = {}, 0
-        for name, s in SEGMENTS:
-            width = 3 * K if s is None else s
+        for name, s_ in SEGMENTS:
+            width = 3 * K if s_ is None else s_
             v = self.table_flat[off:off + n * width]
-            self.views[name] = v.view(n, K, 3) if s is None else v.view(n, width)
+            self.views[name] = v.view(n, K, 3) if s_ is None else v.view(n, width)
             off += n * width
 
-    def step(self, params: dict, vpixels, sh_degree: int, background=(0.0, 0.0, 0.0)):
-        """forward + compositing backward of this rank's view, then the fused reduce; returns the table views."""
-        r, cam = self.rast, self.cameras[self.rank]
-        img = r._forward(params["means"], params["shs"], params["opac"], params["scales"], params["rots"], None, None, cam,
-                         sh_degree, background, None, None)
-        r.backward_render(vpixels, self.n, background)
-        self.h_gacc.barrier(channel=0)    # every rank's accumulator is complete
-        r.backward_gaussians_peers(self.world, self.rank, self.cameras, self.gacc_ptrs, self.table_ptrs, params["means"],
+    def step(self, params: dict, vpixels: dict, sh_degree: int, background=(0.0, 0.0, 0.0), images: dict | None = None):
+        """`vpixels[v]` = cotangent of view v (needed for this rank's views only).  Returns the table views."""
+        r = self.rast
+        for j, v in enumerate(self.mine):
+            r.set_accumulator(self.local_acc[j])  # pointer swap: this view's accumulator
+            img = r._forward(params["means"], params["shs"], params["opac"], params["scales"], params["rots"], None, None,
+                             self.cameras[v], sh_degree, background, None, None)
+            if images is not None:
+                images[v] = img.clone()
+            r.backward_render(vpixels[v], self.n, background)
+        if self.h_gacc is not None:
+            self.h_gacc.barrier(channel=0)   # every rank's accumulators are complete
+        r.backward_gaussians_views(self.cameras, self.view_ptrs, self.world, self.rank, self.table_ptrs, params["means"],
                                    params["shs"], params["opac"], params["scales"], params["rots"], sh_degree)
-        self.h_table.barrier(channel=0)   # every rank's table is complete (and nobody still reads my accumulator)
-        return img, self.views
+        if self.h_table is not None:
+            self.h_table.barrier(channel=0)  # every rank's table is complete (and nobody still reads my accumulators)
+        return self.views
+
+
+class PeerFusedBackward(ViewBatchBackward):
+    """One view per rank (weak scaling): `ViewBatchBackward` with V == world.  `step` takes this rank's cotangent and
+    returns (image of this rank's view, table views)."""
+
+    def __init__(self, rast, n: int, K: int, cameras: list, group=None):
+        super().__init__(rast, n, K, cameras, group)
+        assert self.V == self.world, "one camera (view) per rank"
+
+    def step(self, params: dict, vpixels, sh_degree: int, background=(0.0, 0.0, 0.0)):
+        views = super().step(params, {self.rank: vpixels}, sh_degree, background)
+        return self.rast.image, views

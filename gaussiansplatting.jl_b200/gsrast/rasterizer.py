@@ -316,6 +316,21 @@ class GaussianRasterizer:
             check(_lib.lib().gsr_backward_gaussians_peers(self._h, world, rank, cams, ga, tb, n, sh_degree, K, _ptr(means),
                                                           _ptr(shs), _ptr(opac), _ptr(scales), _ptr(rots), stream), self._h)
 
+    def backward_gaussians_views(self, cameras, view_gacc_ptrs, world, rank, table_ptrs, means, shs, opac, scales, rots,
+                                 sh_degree):
+        """gsr_backward_gaussians_views: per-Gaussian backward of a whole view batch (one accumulator per view, wherever
+        it was rendered), reduced over the views and stored into every rank's table."""
+        n, K = means.shape[0], shs.shape[1]
+        nv = len(cameras)
+        cams = (GsrCamera * nv)(*[c.to_c() for c in cameras])
+        ga = (C.c_void_p * nv)(*[int(p) for p in view_gacc_ptrs])
+        tb = (C.c_void_p * world)(*[int(p) for p in table_ptrs])
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().gsr_backward_gaussians_views(self._h, nv, cams, ga, world, rank, tb, n, sh_degree, K,
+                                                          _ptr(means), _ptr(shs), _ptr(opac), _ptr(scales), _ptr(rots),
+                                                          stream), self._h)
+
     def forward_generation(self) -> int:
         """Number of forwards this handle has run (gsr_forward_generation)."""
         return int(_lib.lib().gsr_forward_generation(self._h))

@@ -172,6 +172,16 @@ GSR_API int gsr_backward_gaussians_peers(GsrHandle *h, int32_t world, int32_t ra
                                  const float *const *peer_gacc, float *const *peer_tables, int64_t n, int32_t sh_degree,
                                  int32_t K, const float *means, const float *shs, const float *opacities,
                                  const float *scales, const float *rotations, void *stream);
+/* The same kernel for a batch of n_views (<= 16) views spread over `world` ranks in any way (several views per rank, or
+ * all on one GPU with world == 1): view v was rendered with cams[v] and its accumulator is view_gacc[v] (one accumulator
+ * per view: gsr_set_accumulator before that view's gsr_backward_render); rank `rank` reduces its slice of the Gaussians
+ * over all n_views and stores the rows into the `world` tables.  On one GPU this replaces n_views accumulating
+ * gsr_backward calls — one pass over the parameters and ONE write of the gradient table per batch instead of n_views
+ * read-modify-write passes.  gsr_backward_gaussians_peers(world, ...) == this with n_views = world. */
+GSR_API int gsr_backward_gaussians_views(GsrHandle *h, int32_t n_views, const GsrCamera *cams, const float *const *view_gacc,
+                                 int32_t world, int32_t rank, float *const *peer_tables, int64_t n, int32_t sh_degree,
+                                 int32_t K, const float *means, const float *shs, const float *opacities,
+                                 const float *scales, const float *rotations, void *stream);
 
 /* update_stats!(strategy, rast.gstate.radii, rast.gstate.∇means_2d, resolution) — strategy.jl:107-136 */
 GSR_API int gsr_update_stats(GsrHandle *h, int64_t n, int32_t *max_radii, float *accum_grad_means2d, float *denom,
