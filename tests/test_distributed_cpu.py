@@ -73,3 +73,20 @@ def test_gradient_table_layout():
             o["vshs"].fill_(2.0)
             assert float(t.flat.sum()) == 2.0 * n * 3 * K  # views alias the flat buffer without overlap
     assert views_for_rank(8, 3, 4) == [3, 7] and views_for_rank(3, 3, 4) == [] and views_for_rank(8, 0, 1) == list(range(8))
+
+
+def test_view_owner_matches_round_robin_sharding():
+    """ViewBatchBackward's accumulator addressing: view v lives on rank v % world at slot v // world — exactly the
+    j-th entry of views_for_rank(V, rank, world) — for every batch size up to the kernel's 16-view limit."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "gaussiansplatting.jl_b200")]
+    from gsrast.distributed import view_owner, views_for_rank
+    for world in (1, 2, 3, 4, 8):
+        for V in range(1, 17):
+            seen = set()
+            for r in range(world):
+                for j, v in enumerate(views_for_rank(V, r, world)):
+                    assert view_owner(v, world) == (r, j)
+                    seen.add(v)
+            assert seen == set(range(V))
+            slots = (V + world - 1) // world
+            assert all(view_owner(v, world)[1] < slots for v in range(V))
