@@ -403,12 +403,16 @@ def main():
             dist.all_reduce(same, op=dist.ReduceOp.MIN)
             identical = bool(same.item())
             del ref0
+        # Both sides of these comparisons carry fp32 atomic-order noise (the oracle-pinned tolerance of either is 1e-4
+        # of the tensor's max, vrot being the sensitive one), so two of them may differ by up to 2e-4.
         worst = max(e_other, e_single or 0.0)
-        parity_check = {"max_rel": worst, "ok": bool(worst <= 1e-4 and identical is not False),
+        parity_check = {"max_rel": worst, "ok": bool(worst <= 2e-4 and identical is not False),
                         "fused_vs_plain_path": e_other, "fused_vs_all_views_on_rank0": e_single,
-                        "tables_bit_identical_across_ranks": identical, "tolerance": 1e-4,
-                        "note": "max over ranks and tensors of ||a-b||inf / ||b||inf; the ORACLE comparison of the same "
-                                "kernels: tools/peers_check.py (profiles/) and tests/test_gpu_parity.py"}
+                        "tables_bit_identical_across_ranks": identical, "tolerance": 2e-4,
+                        "note": "max over ranks and tensors of ||a-b||inf / ||b||inf between two GPU results, each held to "
+                                "1e-4 against the oracle elsewhere (hence 2e-4 here): tools/peers_check.py compares the "
+                                "same kernels with the sum of per-view ORACLE gradients at 1e-4 (profiles/), "
+                                "tests/test_gpu_parity.py the single-GPU forms"}
 
     # ---- end to end: host buffers in, host buffers out --------------------------------------------------------
     e2e = None

@@ -324,9 +324,22 @@ hist_kernel(const uint64_t *__restrict__ keys, const int64_t m, const int depth_
         if (sh[k]) atomicAdd(&ghist[k], sh[k]);
 }
 
-template <int SORT_IPT>
+// digit of a key at `shift`: 64-bit keys are the canonical (tile << 32 | depth bits), sorted through their compact form;
+// 32-bit keys are bare tile ids (the instance sort after the depth pre-sort), sorted as they are
+template <typename KeyT>
+__device__ __forceinline__ uint32_t digit_of(KeyT key, int shift, int depth_bits, uint32_t depth_base);
+template <>
+__device__ __forceinline__ uint32_t digit_of<uint64_t>(uint64_t key, int shift, int depth_bits, uint32_t depth_base) {
+    return (uint32_t)((compact_key(key, depth_bits, depth_base) >> shift) & 255u);
+}
+template <>
+__device__ __forceinline__ uint32_t digit_of<uint32_t>(uint32_t key, int shift, int, uint32_t) {
+    return (key >> shift) & 255u;
+}
+
+template <typename KeyT, int SORT_IPT>
 struct SortSmem {
-    uint64_t keys[SORT_THREADS * SORT_IPT];
+    KeyT keys[SORT_THREADS * SORT_IPT];
     uint32_t vals[SORT_THREADS * SORT_IPT];
     uint32_t whist[SORT_WARPS][256];
     uint32_t excl[256];
@@ -336,15 +349,15 @@ struct SortSmem {
     uint32_t tile;
 };
 
-template <int SORT_IPT, bool BALLOT>
+template <typename KeyT, int SORT_IPT, bool BALLOT>
 __global__ void __launch_bounds__(SORT_THREADS)
-onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, const int64_t m, const int shift,
+onesweep_kernel(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                KeyT *__restrict__ keys_out, uint32_t *__restrict__ vals_out, const int64_t m, const int shift,
                 const int depth_bits, const uint32_t depth_base, const uint32_t *__restrict__ ghist /* [256] */,
                 uint32_t *status /* [tiles][256] */, uint32_t *tile_counter, const int ballot_bits) {
     constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortSmem<SORT_IPT> &S = *reinterpret_cast<SortSmem<SORT_IPT> *>(smem_raw);
+    SortSmem<KeyT, SORT_IPT> &S = *reinterpret_cast<SortSmem<KeyT, SORT_IPT> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) S.tile = atomicAdd(tile_counter, 1u);
 #pragma unroll
@@ -355,7 +368,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
     const int cnt = (int)((m - tile_base) < SORT_TILE ? (m - tile_base) : SORT_TILE);
 
     // ---- load (warp-striped inside each warp's contiguous 512-key chunk) and rank by digit ----------------
-    uint64_t key[SORT_IPT];
+    KeyT key[SORT_IPT];
     uint32_t val[SORT_IPT];
     uint16_t rnk[SORT_IPT];
     uint32_t *whist = S.whist[warp];
@@ -364,14 +377,14 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
     for (int j = 0; j < SORT_IPT; j++) {
         const int local = warp * (32 * SORT_IPT) + j * 32 + lane;
         const bool valid = local < cnt;
-        key[j] = valid ? keys_in[tile_base + local] : ~0ull;
+        key[j] = valid ? keys_in[tile_base + local] : (KeyT)~(KeyT)0;
         val[j] = valid ? vals_in[tile_base + local] : 0u;
     }
 #pragma unroll
     for (int j = 0; j < SORT_IPT; j++) {
         const int local = warp * (32 * SORT_IPT) + j * 32 + lane;
         const bool valid = local < cnt;
-        const uint32_t d = valid ? (uint32_t)((compact_key(key[j], depth_bits, depth_base) >> shift) & 255u) : 0xffffffffu;
+        const uint32_t d = valid ? digit_of<KeyT>(key[j], shift, depth_bits, depth_base) : 0xffffffffu;
         // lanes holding the same digit.  MATCH.ANY's latency is data dependent: on digits made of tile bits
         // (runs of neighbouring tiles from one Gaussian) it is ~3x that on depth bits (ncu: 32 % of the pass's
         // stall samples sit on its consumer), so those passes build the mask from one ballot per digit bit instead
@@ -434,7 +447,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
     for (int j = 0; j < SORT_IPT; j++) {
         const int local = warp * (32 * SORT_IPT) + j * 32 + lane;
         if (local < cnt) {
-            const uint32_t d = (uint32_t)((compact_key(key[j], depth_bits, depth_base) >> shift) & 255u);
+            const uint32_t d = digit_of<KeyT>(key[j], shift, depth_bits, depth_base);
             const uint32_t pos = S.excl[d] + whist[d] + rnk[j];
             S.keys[pos] = key[j];
             S.vals[pos] = val[j];
@@ -466,8 +479,8 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
 
     // ---- stream out the digit runs ------------------------------------------------------------------------
     for (int p = tid; p < cnt; p += SORT_THREADS) {
-        const uint64_t k = S.keys[p];
-        const uint32_t d = (uint32_t)((compact_key(k, depth_bits, depth_base) >> shift) & 255u);
+        const KeyT k = S.keys[p];
+        const uint32_t d = digit_of<KeyT>(k, shift, depth_bits, depth_base);
         const uint32_t gp = S.gbase[d] + (uint32_t)p;
         keys_out[gp] = k;
         vals_out[gp] = S.vals[p];
@@ -508,6 +521,124 @@ tile_ranges_kernel(const int64_t m, const uint64_t *__restrict__ keys, uint32_t 
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// duplicate_with_keys! after the depth pre-sort — utils.jl:85-120, warp-cooperative and load-balanced
+//
+// Emission order is depth order, so the instance sort only needs the TILE of an instance: the key is the bare 32-bit
+// tile id (the canonical 64-bit key is rebuilt from it on demand, materialize_keys_kernel).  A warp takes 32 consecutive
+// Gaussians of the depth order; their output ranges are adjacent, and lane l writes output slots begin + l, begin + 32
+// + l, ...: the owner of a slot is found by a 5-step binary search over the warp's 32 inclusive offsets (shuffles), the
+// tile follows from the slot's position in the owner's rectangle.  Every store is a coalesced 128-byte line whatever
+// the sizes of the rectangles (the per-Gaussian loop writes 32 scattered lines per instruction and runs as long as
+// the largest rectangle of the warp).
+// ----------------------------------------------------------------------------------------------------------
+constexpr int DUPC_THREADS = 256;
+__global__ void __launch_bounds__(DUPC_THREADS)
+duplicate_coop_kernel(const int64_t n, const int32_t grid_x, const int32_t grid_y, const int32_t *__restrict__ radii,
+                      const float2 *__restrict__ means2d, const int32_t *__restrict__ offsets,
+                      const uint32_t *__restrict__ perm, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                      const int passes, uint32_t *__restrict__ ghist) {
+    __shared__ uint32_t sh[4 * 256];
+    for (int k = threadIdx.x; k < passes * 256; k += DUPC_THREADS) sh[k] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    // a CTA walks several 256-Gaussian chunks: its histogram is flushed once (the flush is 256 x passes global atomics per
+    // CTA on the same few hundred addresses — with one chunk per CTA that contention, not the emission, set the time)
+    for (int64_t chunk = blockIdx.x; chunk * DUPC_THREADS < n; chunk += gridDim.x) {
+    const int64_t j = chunk * DUPC_THREADS + threadIdx.x;  // emission slot
+    uint32_t pack = 0, id = 0, end = 0;
+    int cnt = 0;
+    {
+        const int64_t jc = j < n ? j : n - 1;
+        end = (uint32_t)offsets[jc];  // inclusive scan in emission order: monotone, so the search below needs no flags
+        if (j < n) {
+            const int64_t i = (int64_t)perm[j];
+            const int32_t r = radii[i];
+            if (r > 0) {
+                const float2 m = means2d[i];
+                int32_t x0, y0, x1, y1;
+                get_rect(m.x, m.y, r, grid_x, grid_y, x0, y0, x1, y1);
+                cnt = (x1 - x0) * (y1 - y0);
+                pack = (uint32_t)(x1 - x0) | ((uint32_t)x0 << 10) | ((uint32_t)y0 << 20);  // tile grids up to 1023 x 4095
+            }
+            id = (uint32_t)(i + 1);  // 1-based, as the reference emits
+        }
+    }
+    const uint32_t off = end - (uint32_t)cnt;
+    const uint32_t wbegin = __shfl_sync(0xffffffffu, off, 0), wend = __shfl_sync(0xffffffffu, end, 31);
+    for (uint32_t s0 = wbegin; s0 < wend; s0 += 32) {  // warp-uniform trip count
+        const uint32_t s = s0 + lane;
+        const bool valid = s < wend;
+        int g = 0;  // first lane whose inclusive offset exceeds s
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t e = __shfl_sync(0xffffffffu, end, g + step - 1);
+            if (e <= s) g += step;
+        }
+        g = g > 31 ? 31 : g;  // lanes past the warp's range (not stored)
+        const uint32_t gp = __shfl_sync(0xffffffffu, pack, g), go = __shfl_sync(0xffffffffu, off, g);
+        const uint32_t gid = __shfl_sync(0xffffffffu, id, g);
+        uint32_t tile = 0;
+        if (valid) {
+            const uint32_t w = gp & 1023u, t = s - go;
+            const uint32_t q = t / w;
+            tile = ((gp >> 20) + q) * (uint32_t)grid_x + ((gp >> 10) & 1023u) + (t - q * w);
+            keys[s] = tile;
+            vals[s] = gid;
+        }
+        // digit histograms of the tile passes: neighbouring slots are neighbouring tiles — all-distinct low digits
+        // (plain atomics, no conflicts), near-constant high digits (aggregate with MATCH.ANY, fast on few values)
+        if (valid) atomicAdd(&sh[tile & 255u], 1u);
+        for (int p = 1; p < passes; p++) {
+            const uint32_t d = valid ? ((tile >> (8 * p)) & 255u) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[p * 256 + d], (uint32_t)__popc(peers));
+        }
+    }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < passes * 256; k += DUPC_THREADS)
+        if (sh[k]) atomicAdd(&ghist[k], sh[k]);
+}
+
+// identify_tile_range! on bare tile ids
+__global__ void __launch_bounds__(256)
+tile_ranges32_kernel(const int64_t m, const uint32_t *__restrict__ tiles, uint32_t *__restrict__ ranges) {
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= m) return;
+    uint32_t k[4];
+    if (i0 + 4 <= m) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(tiles + i0);
+        k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) k[j] = i0 + j < m ? tiles[i0 + j] : 0u;
+    }
+    uint32_t prev = i0 > 0 ? tiles[i0 - 1] : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int64_t i = i0 + j;
+        if (i >= m) break;
+        const uint32_t tile = k[j];
+        if (i == 0) {
+            ranges[2 * (int64_t)tile] = 0u;
+        } else if (tile != prev) {
+            ranges[2 * (int64_t)prev + 1] = (uint32_t)i;
+            ranges[2 * (int64_t)tile] = (uint32_t)i;
+        }
+        if (i == m - 1) ranges[2 * (int64_t)tile + 1] = (uint32_t)m;
+        prev = tile;
+    }
+}
+
+// the canonical sorted keys (tile << 32 | bits(depth)) from the sorted tile ids and Gaussian ids
+__global__ void __launch_bounds__(256)
+materialize_keys_kernel(const int64_t m, const uint32_t *__restrict__ tiles, const uint32_t *__restrict__ vals,
+                        const float *__restrict__ depths, uint64_t *__restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) keys[i] = ((uint64_t)tiles[i] << 32) | (uint64_t)__float_as_uint(depths[vals[i] - 1u]);
+}
+
 int bit_length(uint64_t x) {
     int b = 0;
     while (x) { b++; x >>= 1; }
@@ -545,8 +676,8 @@ void launch_duplicate(const DevCamera &cam, int64_t n, const GeomPtrs &g, const 
 void launch_presort_keys(int64_t n, const GeomPtrs &g, const SortPlan &plan, uint64_t *keys, uint32_t *vals,
                          uint32_t *ghist, cudaStream_t s) {
     if (n <= 0) return;
-    int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);  // ~8 Gaussians per thread: few histogram flushes
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);  // >= 8 Gaussians per thread: few histogram flushes (contended atomics)
+    if (blocks > 148 * 2) blocks = 148 * 2;
     presort_keys_kernel<<<(unsigned)blocks, 256, 0, s>>>(n, g.radii, g.depths, plan.depth_bits, plan.depth_base,
                                                          plan.passes, keys, vals, ghist);
     count_launch();
@@ -622,10 +753,10 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
     if (m <= 0) return;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(onesweep_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<8>));
-        cudaFuncSetAttribute(onesweep_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<16>));
-        cudaFuncSetAttribute(onesweep_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<8>));
-        cudaFuncSetAttribute(onesweep_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<16>));
+        cudaFuncSetAttribute(onesweep_kernel<uint64_t, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<uint64_t, 8>));
+        cudaFuncSetAttribute(onesweep_kernel<uint64_t, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<uint64_t, 16>));
+        cudaFuncSetAttribute(onesweep_kernel<uint64_t, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<uint64_t, 8>));
+        cudaFuncSetAttribute(onesweep_kernel<uint64_t, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<uint64_t, 16>));
         attr_set = true;
     }
     const int ipt = sort_ipt(plan);
@@ -657,7 +788,7 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
         uint64_t *kdst = to_out ? keys_out : keys_tmp;
         uint32_t *vdst = to_out ? vals_out : vals_tmp;
 #define GSR_ONESWEEP(IPT, BAL)                                                                                       \
-    onesweep_kernel<IPT, BAL><<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem<IPT>), s>>>(                              \
+    onesweep_kernel<uint64_t, IPT, BAL><<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem<uint64_t, IPT>), s>>>(          \
         ksrc, vsrc, kdst, vdst, m, shift, plan.depth_bits, plan.depth_base, ghist + (size_t)p * 256,                    \
         status + (size_t)p * tiles * 256, counters + p, ballot_bits)
         if (ipt == 16) {
@@ -670,6 +801,64 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
         ksrc = kdst;
         vsrc = vdst;
     }
+}
+
+// ---- instance binning on 32-bit tile keys (after the depth pre-sort) -----------------------------------------
+void launch_duplicate_tiles(const DevCamera &cam, int64_t n, const GeomPtrs &g, const int32_t *offsets, const uint32_t *perm,
+                            uint32_t *tiles, uint32_t *vals, const SortPlan &plan, uint32_t *ghist, cudaStream_t s) {
+    if (n <= 0) return;
+    int64_t blocks = (n + DUPC_THREADS - 1) / DUPC_THREADS;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    duplicate_coop_kernel<<<(unsigned)blocks, DUPC_THREADS, 0, s>>>(n, cam.grid_x, cam.grid_y, g.radii, g.means2d, offsets,
+                                                                  perm, tiles, vals, plan.passes, ghist);
+    count_launch();
+}
+
+// plan = tile_only_plan(...): radix passes over the tile id's bits, histograms ready (launch_duplicate_tiles).
+// tiles_in / vals_in are left intact; (tiles_tmp, vals_tmp) is scratch of size m.
+void launch_sort_tiles(const SortPlan &plan, int64_t m, const uint32_t *tiles_in, const uint32_t *vals_in, uint32_t *tiles_out,
+                       uint32_t *vals_out, uint32_t *tiles_tmp, uint32_t *vals_tmp, uint32_t *temp_words, cudaStream_t s) {
+    if (m <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(onesweep_kernel<uint32_t, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<uint32_t, 16>));
+        cudaFuncSetAttribute(onesweep_kernel<uint32_t, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<uint32_t, 8>));
+        attr_set = true;
+    }
+    const int ipt = sort_ipt(plan);
+    const size_t tiles = (size_t)((m + sort_tile_keys(plan) - 1) / sort_tile_keys(plan));
+    uint32_t *ghist = temp_words;
+    uint32_t *status = ghist + (size_t)plan.passes * 256;
+    uint32_t *counters = status + (size_t)plan.passes * tiles * 256;
+    const uint32_t *ksrc = tiles_in, *vsrc = vals_in;
+    for (int p = 0; p < plan.passes; p++) {
+        const int shift = 8 * p;
+        const int digit_bits = plan.tile_bits - shift < 8 ? plan.tile_bits - shift : 8;
+        const bool to_out = ((plan.passes - 1 - p) % 2) == 0;  // the chain ends in (tiles_out, vals_out)
+        uint32_t *kdst = to_out ? tiles_out : tiles_tmp, *vdst = to_out ? vals_out : vals_tmp;
+        if (ipt == 16)
+            onesweep_kernel<uint32_t, 16, true><<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem<uint32_t, 16>), s>>>(
+                ksrc, vsrc, kdst, vdst, m, shift, 0, 0u, ghist + (size_t)p * 256, status + (size_t)p * tiles * 256, counters + p, digit_bits);
+        else
+            onesweep_kernel<uint32_t, 8, true><<<(unsigned)tiles, SORT_THREADS, sizeof(SortSmem<uint32_t, 8>), s>>>(
+                ksrc, vsrc, kdst, vdst, m, shift, 0, 0u, ghist + (size_t)p * 256, status + (size_t)p * tiles * 256, counters + p, digit_bits);
+        count_launch();
+        ksrc = kdst;
+        vsrc = vdst;
+    }
+}
+
+void launch_tile_ranges32(int64_t m, const uint32_t *tiles_sorted, uint32_t *ranges, cudaStream_t s) {
+    if (m <= 0) return;
+    tile_ranges32_kernel<<<(unsigned)((m + 1023) / 1024), 256, 0, s>>>(m, tiles_sorted, ranges);
+    count_launch();
+}
+
+void launch_materialize_keys(int64_t m, const uint32_t *tiles_sorted, const uint32_t *vals_sorted, const float *depths,
+                             uint64_t *keys_sorted, cudaStream_t s) {
+    if (m <= 0) return;
+    materialize_keys_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(m, tiles_sorted, vals_sorted, depths, keys_sorted);
+    count_launch();
 }
 
 void launch_tile_ranges(int64_t m, const uint64_t *keys_sorted, uint32_t *ranges, cudaStream_t s) {

@@ -93,6 +93,14 @@ void launch_sort_pairs(const SortPlan &plan, int64_t m, const uint64_t *keys_in,
                        uint32_t *temp_words, bool hist_ready, cudaStream_t s);
 
 void launch_tile_ranges(int64_t m, const uint64_t *keys_sorted, uint32_t *ranges, cudaStream_t s);
+// instance binning on bare 32-bit tile ids (emission in depth order: the depth pre-sort made the depth bits redundant)
+void launch_duplicate_tiles(const DevCamera &cam, int64_t n, const GeomPtrs &g, const int32_t *offsets, const uint32_t *perm,
+                            uint32_t *tiles, uint32_t *vals, const SortPlan &plan, uint32_t *ghist, cudaStream_t s);
+void launch_sort_tiles(const SortPlan &plan, int64_t m, const uint32_t *tiles_in, const uint32_t *vals_in, uint32_t *tiles_out,
+                       uint32_t *vals_out, uint32_t *tiles_tmp, uint32_t *vals_tmp, uint32_t *temp_words, cudaStream_t s);
+void launch_tile_ranges32(int64_t m, const uint32_t *tiles_sorted, uint32_t *ranges, cudaStream_t s);
+void launch_materialize_keys(int64_t m, const uint32_t *tiles_sorted, const uint32_t *vals_sorted, const float *depths,
+                             uint64_t *keys_sorted, cudaStream_t s);
 
 // both return 0, or -1 when no kernel was compiled for `math_mode`
 int launch_render_forward(int channels, int math_mode, int width, int height, const uint32_t *ranges,

@@ -334,7 +334,8 @@ int gsr_create(const GsrConfig *cfg, GsrHandle **out) {
     h->tplan = tile_only_plan(h->plan);
     {
         const char *e = getenv("GSR_PRESORT");
-        h->presort = !(e && atoi(e) == 0);
+        // (the cooperative duplicate packs a rectangle's origin and width into 10 + 12 + 10 bits)
+        h->presort = !(e && atoi(e) == 0) && h->grid_x <= 1023 && h->grid_y <= 4095;
     }
     const size_t px = (size_t)cfg->width * cfg->height;
     int rc = GSR_OK;
@@ -405,21 +406,33 @@ int gsr_memory_usage(const GsrHandle *h, size_t *bytes) {
     return GSR_OK;
 }
 
+// Writes the buffers of the last forward that the hot path does not keep in the reference's form (see gsr_get_state).
+static int materialize_reference_binning(GsrHandle *h) {
+    if (h->ref_binning_valid || !h->fwd_valid || h->last_n <= 0) return GSR_OK;
+    // With the depth pre-sort the hot path scans and emits in depth order and sorts bare tile ids; the reference's
+    // buffers it does not need in that form — cumsum(tiles_touched) in index order (rasterizer.jl:333), the unsorted keys
+    // / values of duplicate_with_keys! (utils.jl:85-120) and the 64-bit sorted keys (rasterizer.jl:357-372) — are
+    // written here, on demand, for whoever reads the state.  The sort has consumed the depth-order emission by now,
+    // so its buffers are free to hold the reference-order one.
+    cudaStream_t s = h->last_stream;
+    launch_scan_tiles(h->last_n, h->g.tiles_touched, nullptr, h->g.points_offset, h->scan_state, h->total_dev, s);
+    if (h->last_m > 0) {
+        launch_materialize_keys(h->last_m, reinterpret_cast<const uint32_t *>(h->keys_tmp), h->vals_sorted, h->g.depths,
+                                h->keys_sorted, s);
+        launch_duplicate(h->last_cam, h->last_n, h->g, h->g.points_offset, nullptr, h->keys_unsorted, h->vals_unsorted,
+                         h->plan, nullptr, s);
+    }
+    CK(cudaStreamSynchronize(s));
+    h->ref_binning_valid = true;
+    return GSR_OK;
+}
+
 int gsr_get_state(GsrHandle *h, GsrStateViews *v) {
     if (!h || !v) return GSR_EINVAL;
     memset(v, 0, sizeof *v);
-    if (!h->ref_binning_valid && h->fwd_valid && h->last_n > 0) {
-        // With the depth pre-sort the hot path scans and emits in depth order; the reference's intermediate buffers —
-        // cumsum(tiles_touched) in index order (rasterizer.jl:333) and the unsorted keys / values of duplicate_with_keys!
-        // (utils.jl:85-120) — are reproduced here, on demand, for whoever reads the state.  The sort has consumed the
-        // depth-order emission by now, so its buffers are free to hold the reference-order one.
-        cudaStream_t s = h->last_stream;
-        launch_scan_tiles(h->last_n, h->g.tiles_touched, nullptr, h->g.points_offset, h->scan_state, h->total_dev, s);
-        if (h->last_m > 0)
-            launch_duplicate(h->last_cam, h->last_n, h->g, h->g.points_offset, nullptr, h->keys_unsorted, h->vals_unsorted,
-                             h->plan, nullptr, s);
-        CK(cudaStreamSynchronize(s));
-        h->ref_binning_valid = true;
+    {
+        const int rc = materialize_reference_binning(h);
+        if (rc) return rc;
     }
     v->n = h->last_n;
     v->n_rendered = h->last_m;
@@ -507,22 +520,43 @@ static int forward_impl(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t s
     rc = ensure_binning(h, m);
     if (rc) return rc;
 
-    const SortPlan &iplan = h->presort ? h->tplan : h->plan;  // instance sort: tile digits only after the pre-sort
-    {
-        StageTimer tm(h, s, GSR_STAGE_DUPLICATE);
-        uint32_t *ghist = sort_prepare(iplan, m, h->sort_temp, s);
-        launch_duplicate(dc, n, h->g, h->presort ? h->offsets_sorted : h->g.points_offset, h->presort ? h->pv[1] : nullptr,
-                         h->keys_unsorted, h->vals_unsorted, iplan, ghist, s);
-    }
-    {
-        StageTimer tm(h, s, GSR_STAGE_SORT);
-        launch_sort_pairs(iplan, m, h->keys_unsorted, h->vals_unsorted, h->keys_sorted, h->vals_sorted, h->keys_tmp,
-                          h->vals_tmp, h->sort_temp, /*hist_ready=*/true, s);
-    }
-    {
-        StageTimer tm(h, s, GSR_STAGE_RANGES);
-        CK(cudaMemsetAsync(h->ranges, 0, 2 * (size_t)h->n_tiles * sizeof(uint32_t), s));  // rasterizer.jl:375
-        launch_tile_ranges(m, h->keys_sorted, h->ranges, s);
+    if (h->presort) {
+        // Emission is in depth order, so an instance's sort key is its bare 32-bit tile id: 8 bytes per instance through
+        // duplicate / the tile-digit passes / the range scan instead of 12.  The three 64-bit key buffers serve as 32-bit
+        // scratch (unsorted | pass scratch in the halves of keys_unsorted, sorted tile ids in keys_tmp); keys_sorted holds
+        // the canonical 64-bit keys once gsr_get_state asks for them.
+        uint32_t *t_in = reinterpret_cast<uint32_t *>(h->keys_unsorted), *t_tmp = t_in + h->cap_m;
+        uint32_t *t_out = reinterpret_cast<uint32_t *>(h->keys_tmp);
+        {
+            StageTimer tm(h, s, GSR_STAGE_DUPLICATE);
+            uint32_t *ghist = sort_prepare(h->tplan, m, h->sort_temp, s);
+            launch_duplicate_tiles(dc, n, h->g, h->offsets_sorted, h->pv[1], t_in, h->vals_unsorted, h->tplan, ghist, s);
+        }
+        {
+            StageTimer tm(h, s, GSR_STAGE_SORT);
+            launch_sort_tiles(h->tplan, m, t_in, h->vals_unsorted, t_out, h->vals_sorted, t_tmp, h->vals_tmp, h->sort_temp, s);
+        }
+        {
+            StageTimer tm(h, s, GSR_STAGE_RANGES);
+            CK(cudaMemsetAsync(h->ranges, 0, 2 * (size_t)h->n_tiles * sizeof(uint32_t), s));  // rasterizer.jl:375
+            launch_tile_ranges32(m, t_out, h->ranges, s);
+        }
+    } else {
+        {
+            StageTimer tm(h, s, GSR_STAGE_DUPLICATE);
+            uint32_t *ghist = sort_prepare(h->plan, m, h->sort_temp, s);
+            launch_duplicate(dc, n, h->g, h->g.points_offset, nullptr, h->keys_unsorted, h->vals_unsorted, h->plan, ghist, s);
+        }
+        {
+            StageTimer tm(h, s, GSR_STAGE_SORT);
+            launch_sort_pairs(h->plan, m, h->keys_unsorted, h->vals_unsorted, h->keys_sorted, h->vals_sorted, h->keys_tmp,
+                              h->vals_tmp, h->sort_temp, /*hist_ready=*/true, s);
+        }
+        {
+            StageTimer tm(h, s, GSR_STAGE_RANGES);
+            CK(cudaMemsetAsync(h->ranges, 0, 2 * (size_t)h->n_tiles * sizeof(uint32_t), s));  // rasterizer.jl:375
+            launch_tile_ranges(m, h->keys_sorted, h->ranges, s);
+        }
     }
     {
         StageTimer tm(h, s, GSR_STAGE_RENDER_FWD);
@@ -1038,7 +1072,9 @@ int gsr_sort_pairs(GsrHandle *h, const uint64_t *keys_in_dev, const uint32_t *va
     if (m == 0) return GSR_OK;
     if (!keys_in_dev || !vals_in_dev || !keys_out_dev || !vals_out_dev)
         return fail(h, GSR_EINVAL, "gsr_sort_pairs: null argument");
-    int rc = ensure_binning(h, m);
+    int rc = materialize_reference_binning(h);  // this call reuses the pass scratch that still holds the sorted tile ids
+    if (rc) return rc;
+    rc = ensure_binning(h, m);
     if (rc) return rc;
     sort_prepare(h->plan, m, h->sort_temp, static_cast<cudaStream_t>(stream));
     launch_sort_pairs(h->plan, m, keys_in_dev, vals_in_dev, keys_out_dev, vals_out_dev, h->keys_tmp, h->vals_tmp,
