@@ -369,9 +369,23 @@ def main():
     ms_per_step = total_ms / args.steps
     units_per_step = 1 if kind == "batch" else world  # batches, or views over all ranks
     value = units_per_step * args.steps / (total_ms * 1e-3)
-    alt_value = None
+    alt_value, scatter_value, scatter_err = None, None, None
     if fused is not None:  # the same step through the other exchange path, for comparison
         alt_value = units_per_step * args.steps / (timed(step_plain, args.steps, 3) * 1e-3)
+    if fused is not None and world > 1 and not args.no_parity_check:
+        # ... and with reduce-scatter semantics (every rank keeps the reduced rows of ITS Gaussian slice only, what a
+        # Gaussian-sharded optimizer consumes): the same kernel without the all-gather half of the exchange
+        rast_s = GaussianRasterizer(width=W, height=H, mode=mode, math_mode=args.math, device=dev)
+        fs = ViewBatchBackward(rast_s, n, K, cams, scatter_only=True)
+        scatter_value = units_per_step * args.steps / (timed(lambda: fs.step(d, vp_mine, deg), args.steps, 3) * 1e-3)
+        fused.step(d, vp_mine, deg)
+        torch.cuda.synchronize()
+        lo_g, hi_g = fs.slice_rows()
+        es = torch.tensor([max(float((fs.views[k][lo_g:hi_g].double() - fused.views[k][lo_g:hi_g].double()).abs().max()
+                                     / fused.views[k].double().abs().max().clamp_min(1e-30)) for k in fused.views)], device=dev)
+        dist.all_reduce(es, op=dist.ReduceOp.MAX)
+        scatter_err = float(es.item())
+        del fs, rast_s
 
     # ---- parity of the multi-view / multi-GPU value path, outside the timed region ------------------------------
     parity_check = None
@@ -507,6 +521,7 @@ def main():
                    "math_mode": args.math, "views_per_step": V, "views_per_step_per_gpu": len(mine),
                    "parallelism": f"view-sharded x{world}", "gradient_reduction": reduction,
                    "value_through_the_plain_path": alt_value,
+                   "value_with_reduce_scatter_only": scatter_value, "reduce_scatter_slice_vs_allreduce_table": scatter_err,
                    "l2": f"inputs larger than L2: {4 * n * (11 + 3 * K) / 1e6:.0f} MB parameters"
                          + ("" if kind == "render" else " + as many of gradients") + " + per-view state vs 126 MB L2"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "parity_check": parity_check,

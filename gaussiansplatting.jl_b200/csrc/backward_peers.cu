@@ -188,6 +188,7 @@ backward_gaussians_peers_kernel(const PeerArgs A) {
         // ---- store the reduced row into EVERY rank's table (P2P stores) ---------------------------------------
         for (int p = 0; p < A.world; p++) {
             float *tb = A.table[p];
+            if (!tb) continue;  // a rank without a table pointer does not receive the rows (reduce-scatter only)
             *reinterpret_cast<float4 *>(tb + 4 * i) = make_float4(vq[0], vq[1], vq[2], vq[3]);
             float *pm = tb + 4 * n + 3 * i, *ps = tb + 7 * n + 3 * i;
             pm[0] = vmean[0]; pm[1] = vmean[1]; pm[2] = vmean[2];
@@ -211,11 +212,12 @@ backward_gaussians_peers_kernel(const PeerArgs A) {
             }
             const float4 val = make_float4(vv[0], vv[1], vv[2], vv[3]);
             for (int p = 0; p < A.world; p++)
-                *(reinterpret_cast<float4 *>(A.table[p] + 11 * n + block0 * row) + q) = val;
+                if (A.table[p]) *(reinterpret_cast<float4 *>(A.table[p] + 11 * n + block0 * row) + q) = val;
         }
         for (int64_t e = (nq << 2) + tid; e < span; e += BP_THREADS) {
             const int gg = (int)(e / row), rr = (int)(e - (int64_t)gg * row);
-            for (int p = 0; p < A.world; p++) A.table[p][11 * n + block0 * row + e] = s_vsh[gg * stride + rr];
+            for (int p = 0; p < A.world; p++)
+                if (A.table[p]) A.table[p][11 * n + block0 * row + e] = s_vsh[gg * stride + rr];
         }
     }
 }

@@ -676,8 +676,8 @@ void launch_duplicate(const DevCamera &cam, int64_t n, const GeomPtrs &g, const 
 void launch_presort_keys(int64_t n, const GeomPtrs &g, const SortPlan &plan, uint64_t *keys, uint32_t *vals,
                          uint32_t *ghist, cudaStream_t s) {
     if (n <= 0) return;
-    int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);  // >= 8 Gaussians per thread: few histogram flushes (contended atomics)
-    if (blocks > 148 * 2) blocks = 148 * 2;
+    int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);  // ~8 Gaussians per thread: few histogram flushes
+    if (blocks > 148 * 8) blocks = 148 * 8;
     presort_keys_kernel<<<(unsigned)blocks, 256, 0, s>>>(n, g.radii, g.depths, plan.depth_bits, plan.depth_base,
                                                          plan.passes, keys, vals, ghist);
     count_launch();

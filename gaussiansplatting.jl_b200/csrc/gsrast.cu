@@ -744,8 +744,9 @@ int gsr_backward_gaussians_views(GsrHandle *h, int32_t n_views, const GsrCamera 
         a.cams[v].blur_eps = h->cfg.blur_eps;
         a.gacc[v] = view_gacc[v];
     }
+    if (!peer_tables[rank]) return fail(h, GSR_EINVAL, "gsr_backward_gaussians_views: the calling rank's table pointer is null");
     for (int p = 0; p < world; p++) {
-        if (!peer_tables[p]) return fail(h, GSR_EINVAL, "gsr_backward_gaussians_views: null table pointer");
+        if (!peer_tables[p]) continue;  // that rank keeps only its own slice (reduce-scatter semantics)
         if (reinterpret_cast<uintptr_t>(peer_tables[p]) & 15)
             return fail(h, GSR_EINVAL, "gsr_backward_gaussians_views: tables must be 16-byte aligned");
         a.table[p] = peer_tables[p];

@@ -98,8 +98,11 @@ class ViewBatchBackward:
     `gsr_backward` calls: the parameters are read once and the gradient table is written once instead of V
     read-modify-write passes.  Result == sum over the V views of ∇rasterize, same layout as `GradientTable`."""
 
-    def __init__(self, rast, n: int, K: int, cameras: list, group=None):
+    def __init__(self, rast, n: int, K: int, cameras: list, group=None, scatter_only: bool = False):
+        """scatter_only: every rank ends with the reduced rows of its own Gaussian slice `slice_rows()` only (reduce-
+        scatter semantics, for a Gaussian-sharded optimizer) instead of the full replicated table (all-reduce)."""
         self.rast, self.n, self.K, self.cameras = rast, n, K, list(cameras)
+        self.scatter_only = bool(scatter_only)
         self.V = len(self.cameras)
         assert 1 <= self.V <= 16, "1..16 views per batch"
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -123,6 +126,8 @@ class ViewBatchBackward:
             self.table_flat = torch.empty(n * per, dtype=torch.float32, device=dev)
             self.h_gacc = self.h_table = None
             bases, self.table_ptrs = [self.gacc.data_ptr()], [self.table_flat.data_ptr()]
+        if self.scatter_only:
+            self.table_ptrs = [p if r == self.rank else 0 for r, p in enumerate(self.table_ptrs)]
         stride = n * self.af * 4
         self.view_ptrs = [bases[view_owner(v, self.world)[0]] + view_owner(v, self.world)[1] * stride for v in range(self.V)]
         self.local_acc = [self.gacc[j * n * self.af:(j + 1) * n * self.af] for j in range(slots)]
@@ -132,6 +137,13 @@ class ViewBatchBackward:
             v = self.table_flat[off:off + n * width]
             self.views[name] = v.view(n, K, 3) if s_ is None else v.view(n, width)
             off += n * width
+
+    def slice_rows(self) -> tuple[int, int]:
+        """[lo, hi): the Gaussians whose gradient rows this rank reduces (the kernel's slicing: 64-aligned chunks)."""
+        chunk = (self.n + self.world - 1) // self.world
+        chunk = (chunk + 63) // 64 * 64
+        lo = min(self.rank * chunk, self.n)
+        return lo, min(lo + chunk, self.n)
 
     def step(self, params: dict, vpixels: dict, sh_degree: int, background=(0.0, 0.0, 0.0), images: dict | None = None):
         """`vpixels[v]` = cotangent of view v (needed for this rank's views only).  Returns the table views."""

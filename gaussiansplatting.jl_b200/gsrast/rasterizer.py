@@ -324,7 +324,7 @@ class GaussianRasterizer:
         nv = len(cameras)
         cams = (GsrCamera * nv)(*[c.to_c() for c in cameras])
         ga = (C.c_void_p * nv)(*[int(p) for p in view_gacc_ptrs])
-        tb = (C.c_void_p * world)(*[int(p) for p in table_ptrs])
+        tb = (C.c_void_p * world)(*[(int(p) or None) for p in table_ptrs])  # 0 -> NULL: that rank receives nothing
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         with torch.cuda.device(self.device):
             check(_lib.lib().gsr_backward_gaussians_views(self._h, nv, cams, ga, world, rank, tb, n, sh_degree, K,

@@ -177,7 +177,9 @@ GSR_API int gsr_backward_gaussians_peers(GsrHandle *h, int32_t world, int32_t ra
  * per view: gsr_set_accumulator before that view's gsr_backward_render); rank `rank` reduces its slice of the Gaussians
  * over all n_views and stores the rows into the `world` tables.  On one GPU this replaces n_views accumulating
  * gsr_backward calls — one pass over the parameters and ONE write of the gradient table per batch instead of n_views
- * read-modify-write passes.  gsr_backward_gaussians_peers(world, ...) == this with n_views = world. */
+ * read-modify-write passes.  gsr_backward_gaussians_peers(world, ...) == this with n_views = world.
+ * peer_tables[p] == NULL for p != rank: rank p does not receive this rank's rows — with only its own pointer set, every
+ * rank ends with the reduced rows of ITS slice only (reduce-scatter; a Gaussian-sharded optimizer needs no more). */
 GSR_API int gsr_backward_gaussians_views(GsrHandle *h, int32_t n_views, const GsrCamera *cams, const float *const *view_gacc,
                                  int32_t world, int32_t rank, float *const *peer_tables, int64_t n, int32_t sh_degree,
                                  int32_t K, const float *means, const float *shs, const float *opacities,
