@@ -10,8 +10,9 @@ import re
 import sys
 from collections import OrderedDict
 
-STAGE_OF = [("preprocess_kernel", "preprocess"), ("scan_kernel", "scan"), ("duplicate_kernel", "duplicate"),
-            ("onesweep_kernel", "sort"), ("hist_kernel", "sort"), ("tile_ranges_kernel", "ranges"),
+STAGE_OF = [("preprocess_kernel", "preprocess"), ("presort_keys_kernel", "presort"), ("onesweep_kernel<unsigned long", "presort"),
+            ("scan_kernel", "scan"), ("duplicate_coop_kernel", "duplicate"), ("duplicate_kernel", "duplicate"),
+            ("onesweep_kernel", "sort"), ("hist_kernel", "sort"), ("tile_ranges", "ranges"),
             ("render_fwd", "render_fwd"), ("render_bwd", "render_bwd"), ("backward_gaussians", "gauss_bwd")]
 
 
@@ -35,7 +36,7 @@ def main():
             b = v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
             d["rd" if "read" in m else "wr"] += b
     total = sum(d["us"] for d in per.values())
-    out = [f"# ncu launch list, {tag} (C2: 1M Gaussians, SH3, 1920x1088, :rgbd, math fast)",
+    out = [f"# ncu launch list, {tag} (C2: 1M Gaussians, SH3, 1920x1088, :rgbd, default strict math)",
            f"# command: {cmd}",
            "# per-launch times are cold-cache and serialised: compare SHARES with bench.py's `stages`, not absolutes",
            f"{'kernel':44s} {'launches':>8s} {'avg_us':>9s} {'share%':>7s} {'dram_rd_MB':>11s} {'dram_wr_MB':>11s}"]

@@ -126,6 +126,20 @@ for V in ([world] if big else [world, min(16, 2 * world)]):
         case["nccl_path_vs_oracle_sum"] = rel_errs(ref_nccl, ref, keep)
         case["ambiguous_gaussians_excluded"] = int(amb.sum())
         ok = ok and max(case["fused_vs_oracle_sum"].values()) <= 1e-4 and max(case["nccl_path_vs_oracle_sum"].values()) <= 1e-4
+    if world > 1:  # reduce-scatter form: every rank keeps the reduced rows of its own slice only
+        rast_c = GaussianRasterizer(width=sc.width, height=sc.height, mode=mode, device=dev)
+        fs = ViewBatchBackward(rast_c, n, K, cams, scatter_only=True)
+        fs.table_flat.fill_(float("nan"))  # rows outside the slice must stay untouched
+        sv = fs.step(params, vp_dev, deg)
+        torch.cuda.synchronize()
+        lo, hi = fs.slice_rows()
+        e = max(float((sv[k][lo:hi].double() - views[k][lo:hi].double()).abs().max() / views[k].double().abs().max().clamp_min(1e-30))
+                for k in KEYS)
+        untouched = all(bool(torch.isnan(sv[k][:lo]).all()) and bool(torch.isnan(sv[k][hi:]).all()) for k in KEYS)
+        case["scatter_only_slice_vs_fused"] = e
+        case["scatter_only_rows_outside_slice_untouched"] = untouched
+        ok = ok and e <= 2e-5 and untouched
+        del fs, rast_c
     case["ms_nccl_path"] = timeit(step_nccl)
     case["ms_fused"] = timeit(lambda: fused.step(params, vp_dev, deg))
     report["cases"].append(case)
