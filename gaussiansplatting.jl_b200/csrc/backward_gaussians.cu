@@ -90,25 +90,18 @@ backward_gaussians_kernel(const DevCamera cam, const int64_t n, const int sh_deg
             }
             for (int e = 0; e < row; e++) vsh[e] = 0.f;
         } else {
-            const float *acc = g.gacc + i * (int64_t)AF;
-            const float4 a0 = *reinterpret_cast<const float4 *>(acc);
-            const float4 a1 = *reinterpret_cast<const float4 *>(acc + 4);
-            const float4 a2 = *reinterpret_cast<const float4 *>(acc + 8);
+            const AccRow a = load_acc_row(g.gacc + i * (int64_t)AF, channels);
             // the compositing backward accumulates moments (render.cu): convert to the reference's cotangents
             //   v_mean2d = conic * (Sx, Sy)             render.jl:269-272
             //   v_conic  = 0.5 * (Sxx, Sxy, Syy)        render.jl:264-268
             //   v_opacity = (sum e*v_alpha) / opacity   render.jl:273  (e = opacity*G)
             const float ca = g.conics[3 * i], cb = g.conics[3 * i + 1], cc = g.conics[3 * i + 2];
-            const float vm2[2] = {ca * a0.x + cb * a0.y, cb * a0.x + cc * a0.y};
-            const float vcn[3] = {0.5f * a0.z, 0.5f * a0.w, 0.5f * a1.x};
+            const float vm2[2] = {ca * a.sx + cb * a.sy, cb * a.sx + cc * a.sy};
+            const float vcn[3] = {0.5f * a.sxx, 0.5f * a.sxy, 0.5f * a.syy};
             const float op = (RAW && ps.raw_opacity) ? act_sigmoid(opac[i]) : opac[i];
-            float vop = op > 0.0f ? a1.y / op : 0.0f;
+            float vop = op > 0.0f ? a.se / op : 0.0f;
             if (RAW && ps.raw_opacity) vop *= op * (1.0f - op);  // pullback of sigmoid (rasterizer.jl:229)
-            float vcol[8] = {a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, 0.f, 0.f};
-            if (channels > 5) {
-                const float4 a3 = *reinterpret_cast<const float4 *>(acc + 12);
-                vcol[6] = a3.x; vcol[7] = a3.y;
-            }
+            const float *vcol = a.f;
             g.grad_means2d[i] = make_float2(vm2[0], vm2[1]);
             put<ACC>(vopac + i, vop);
 

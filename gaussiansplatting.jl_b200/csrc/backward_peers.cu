@@ -6,8 +6,8 @@
 //
 // This kernel does both steps at once over peer-mapped (symmetric) memory:
 //   * rank r owns the Gaussian slice S_r = [lo, hi);
-//   * for every Gaussian of its slice it LOADS the 48/64-byte moment accumulator of EVERY rank's view straight
-//     from that rank's HBM over NVLink (P2P loads: (G-1)/G x 48 B/Gaussian instead of 236 B), applies that view's
+//   * for every Gaussian of its slice it LOADS the 64/80-byte moment accumulator of EVERY view straight
+//     from that rank's HBM over NVLink (P2P loads: (G-1)/G x 64 B/Gaussian instead of 236 B), applies that view's
 //     ∇project / ∇spherical_harmonics chain (cameras of all views are kernel parameters; Gaussian parameters are
 //     replicated) and sums the G per-view gradients in registers / shared memory in a fixed order (deterministic,
 //     unlike an all-reduce);
@@ -29,7 +29,7 @@ namespace {
 
 using namespace gchain;  // grad_chain.cuh: the pullbacks shared with backward_gaussians.cu
 
-// flags word in accumulator slot AF-1: bit 3 = visible (radii > 0), bits 0..2 = clamped rgb
+// flags word in accumulator slot GSR_ACC_FLAGS_SLOT: bit 3 = visible (radii > 0), bits 0..2 = clamped rgb
 __global__ void __launch_bounds__(256)
 pack_flags_kernel(const int64_t n, const int AF, const int32_t *__restrict__ radii, const uint8_t *__restrict__ clamped,
                   float *__restrict__ gacc) {
@@ -37,7 +37,7 @@ pack_flags_kernel(const int64_t n, const int AF, const int32_t *__restrict__ rad
     if (i >= n) return;
     uint32_t f = 0;
     if (radii[i] > 0) f = 8u | (clamped[3 * i] ? 1u : 0u) | (clamped[3 * i + 1] ? 2u : 0u) | (clamped[3 * i + 2] ? 4u : 0u);
-    gacc[i * (int64_t)AF + AF - 1] = __uint_as_float(f);
+    gacc[i * (int64_t)AF + GSR_ACC_FLAGS_SLOT] = __uint_as_float(f);
 }
 
 // rast.gstate.∇means_2d of the LOCAL view for all Gaussians (strategy.jl:85-86 reads it): conic * (Sx, Sy)
@@ -48,7 +48,8 @@ grad_means2d_kernel(const int64_t n, const int AF, const int32_t *__restrict__ r
     if (i >= n) return;
     float2 v = make_float2(0.f, 0.f);
     if (radii[i] > 0) {
-        const float sx = gacc[i * (int64_t)AF], sy = gacc[i * (int64_t)AF + 1];
+        const double2 sxy = *reinterpret_cast<const double2 *>(gacc + i * (int64_t)AF);
+        const float sx = (float)sxy.x, sy = (float)sxy.y;
         const float ca = conics[3 * i], cb = conics[3 * i + 1], cc = conics[3 * i + 2];
         v = make_float2(ca * sx + cb * sy, cb * sx + cc * sy);
     }
@@ -107,18 +108,12 @@ backward_gaussians_peers_kernel(const PeerArgs A) {
 
         for (int v = 0; v < A.n_views; v++) {
             // ---- this view's accumulator row, straight from the memory of the rank that rendered it (P2P load) ----
-            const float *acc = A.gacc[v] + i * (int64_t)AF;
-            const float4 a0 = *reinterpret_cast<const float4 *>(acc);
-            const float4 a1 = *reinterpret_cast<const float4 *>(acc + 4);
-            const float4 a2 = *reinterpret_cast<const float4 *>(acc + 8);
-            float4 a3 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (AF > 12) a3 = *reinterpret_cast<const float4 *>(acc + 12);
-            const uint32_t flags = __float_as_uint(AF > 12 ? a3.w : a2.w);
+            const AccRow a = load_acc_row(A.gacc[v] + i * (int64_t)AF, A.channels);
+            const uint32_t flags = a.flags;
             if (!(flags & 8u)) continue;  // culled in view v (projection.jl:172-176)
             const PeerCamera &cam = A.cams[v];
             const float *R = cam.R, *t = cam.t;
-            float vcol[8] = {a1.z, a1.w, a2.x, a2.y, 0.f, a2.w, a3.x, a3.y};
-            if (A.channels <= 5) vcol[5] = 0.f;  // slot 11 holds the flags when AF == 12
+            const float *vcol = a.f;
 
             float mc[3], Sc[9], T1[9];
 #pragma unroll
@@ -130,9 +125,9 @@ backward_gaussians_peers_kernel(const PeerArgs A) {
             float ca, cb, cc;
             conic_from_cov(P, Sc, cam.blur_eps, ca, cb, cc);
             // moments -> cotangents (render.jl:264-273)
-            const float vm2[2] = {ca * a0.x + cb * a0.y, cb * a0.x + cc * a0.y};
-            const float vcn[3] = {0.5f * a0.z, 0.5f * a0.w, 0.5f * a1.x};
-            vop += op > 0.0f ? a1.y / op : 0.0f;
+            const float vm2[2] = {ca * a.sx + cb * a.sy, cb * a.sx + cc * a.sy};
+            const float vcn[3] = {0.5f * a.sxx, 0.5f * a.sxy, 0.5f * a.syy};
+            vop += op > 0.0f ? a.se / op : 0.0f;
             float vS2[4], vSc[9], vmc[3];
             grad_inverse2(ca, cb, cc, vcn, vS2);
             grad_perspective(P, mc, Sc, vS2, vm2, vSc, vmc);

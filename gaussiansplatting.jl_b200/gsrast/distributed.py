@@ -91,7 +91,7 @@ class ViewBatchBackward:
     """A batch of V views (V <= 16) sharded round-robin over the ranks — several views per rank, or all of them on one
     GPU — with ONE fused per-Gaussian backward + exchange per batch (csrc/backward_peers.cu, gsr_backward_gaussians_views).
 
-    Every view gets its own moment accumulator (48/64 B per Gaussian).  After this rank's forwards and compositing
+    Every view gets its own moment accumulator (64 / 80 B per Gaussian).  After this rank's forwards and compositing
     backwards, rank r reduces ITS slice of the Gaussians over all V accumulators — loading the other ranks' rows over
     NVLink — and stores the finished rows into every rank's table: compute + reduce-scatter + all-gather in one kernel,
     once per batch.  On a single GPU (world == 1, no process group needed) the same kernel replaces V accumulating
@@ -110,7 +110,7 @@ class ViewBatchBackward:
         self.world = dist.get_world_size(self.group) if multi else 1
         self.rank = dist.get_rank(self.group) if multi else 0
         self.mine = views_for_rank(self.V, self.rank, self.world)
-        self.af = 12 if rast.channels <= 6 else 16
+        self.af = 16 if rast.channels <= 6 else 20  # csrc/common.cuh acc_floats
         dev = rast.device
         slots = (self.V + self.world - 1) // self.world  # accumulators per rank (same on every rank: symmetric)
         per = 4 + 3 + 3 + 1 + 3 * K

@@ -295,7 +295,7 @@ class GaussianRasterizer:
         if gacc is None:
             check(_lib.lib().gsr_set_accumulator(self._h, None, 0), self._h)
         else:
-            af = 12 if self.channels <= 6 else 16
+            af = 16 if self.channels <= 6 else 20  # csrc/common.cuh acc_floats
             check(_lib.lib().gsr_set_accumulator(self._h, _ptr(gacc), gacc.numel() // af), self._h)
         self._ext_gacc = gacc
 

@@ -158,7 +158,7 @@ GSR_API int gsr_backward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t 
 
 /* ---- multi-GPU: per-Gaussian backward fused with the cross-GPU gradient reduction over peer memory -----------
  * (not in the reference, which is single-GPU; semantics = sum over the ranks' views of ∇rasterize)
- * gsr_set_accumulator: make the handle keep its per-Gaussian accumulator ([capacity][12 or 16] floats) in
+ * gsr_set_accumulator: make the handle keep its per-Gaussian accumulator ([capacity][16 or 20] floats: 64 B per Gaussian for :rgb / :rgbd, 80 B for :rgbdn) in
  *   caller-provided memory, e.g. a symmetric / peer-mapped allocation (NULL, 0 restores the private buffer).
  * gsr_backward_render: first half of ∇rasterize — zero-fill + ∇render! into the accumulator (+ ∇means_2d).
  * gsr_backward_gaussians_peers: second half for `world` ranks at once.  Rank `rank` owns the Gaussian slice
