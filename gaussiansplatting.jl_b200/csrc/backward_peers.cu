@@ -48,8 +48,8 @@ grad_means2d_kernel(const int64_t n, const int AF, const int32_t *__restrict__ r
     if (i >= n) return;
     float2 v = make_float2(0.f, 0.f);
     if (radii[i] > 0) {
-        const double2 sxy = *reinterpret_cast<const double2 *>(gacc + i * (int64_t)AF);
-        const float sx = (float)sxy.x, sy = (float)sxy.y;
+        const float2 sxy = *reinterpret_cast<const float2 *>(gacc + i * (int64_t)AF);
+        const float sx = sxy.x, sy = sxy.y;
         const float ca = conics[3 * i], cb = conics[3 * i + 1], cc = conics[3 * i + 2];
         v = make_float2(ca * sx + cb * sy, cb * sx + cc * sy);
     }

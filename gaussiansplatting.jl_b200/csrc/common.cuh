@@ -30,15 +30,16 @@ struct DevCamera {
 //   float4 q3 = {f6, f7, 0, 0}              (channels == 8 -> 4 quads, 64 B)
 __host__ __device__ constexpr int rec_quads(int channels) { return channels <= 6 ? 3 : 4; }
 // Per-Gaussian gradient accumulator filled by the backward compositing kernel, moment form.  In 4-byte slots:
-//   0-9   five DOUBLES  S v_sigma*dx, S v_sigma*dy, S v_sigma*dx^2, S v_sigma*dx*dy, S v_sigma*dy^2
-//   10    float         S e*v_alpha                         11   flags word (multi-GPU: visible | clamped rgb)
+//   0-1   floats        S v_sigma*dx, S v_sigma*dy                       (-> v_mean2d = conic * (Sx, Sy))
+//   2-7   three DOUBLES S v_sigma*dx^2, S v_sigma*dx*dy, S v_sigma*dy^2  (-> v_conic)
+//   8     float         S e*v_alpha         9  flags word (multi-GPU: visible | clamped rgb)        10-11 pad
 //   12-15 floats        v_f0 .. v_f3 (rgb, depth)           16-18 v_f5 .. v_f7 (normal; channels == 8 only), 19 pad
-// The five geometric moments feed the ill-conditioned part of the chain (the rotation / scale gradients of elongated
-// Gaussians are differences of large terms): summed with fp32 atomics over the thousands of rows a large splat receives,
-// their order-dependent rounding alone moved `vrot` by up to 1.1e-4 of its maximum between runs at C2 (60 runs:
-// median 4e-5).  fp64 REDs make the sums order-independent to ~1e-13; every per-row partial sum stays fp32.
+// The second moments feed the ill-conditioned part of the chain (the rotation / scale gradients of elongated Gaussians
+// are differences of large terms): summed with fp32 atomics over the thousands of rows a large splat receives, their
+// order-dependent rounding alone moved `vrot` by up to 1e-4 of its maximum between runs at C2 (60 runs: median 4e-5).
+// fp64 REDs make those sums order-independent to ~1e-13; every per-row partial sum stays fp32.
 __host__ __device__ constexpr int acc_floats(int channels) { return channels <= 6 ? 16 : 20; }
-#define GSR_ACC_FLAGS_SLOT 11
+#define GSR_ACC_FLAGS_SLOT 9
 
 struct AccRow {
     float sx, sy, sxx, sxy, syy, se;
@@ -47,14 +48,15 @@ struct AccRow {
 };
 __device__ __forceinline__ AccRow load_acc_row(const float *acc, const int channels) {
     AccRow r;
-    const double2 d0 = *reinterpret_cast<const double2 *>(acc);      // 128-bit loads (rows are 16-byte aligned)
+    const float4 q0 = *reinterpret_cast<const float4 *>(acc);       // 128-bit loads (rows are 16-byte aligned)
     const double2 d1 = *reinterpret_cast<const double2 *>(acc + 4);
     const float4 q2 = *reinterpret_cast<const float4 *>(acc + 8);
     const float4 q3 = *reinterpret_cast<const float4 *>(acc + 12);
-    r.sx = (float)d0.x; r.sy = (float)d0.y; r.sxx = (float)d1.x; r.sxy = (float)d1.y;
-    r.syy = (float)__hiloint2double(__float_as_int(q2.y), __float_as_int(q2.x));
-    r.se = q2.z;
-    r.flags = __float_as_uint(q2.w);
+    r.sx = q0.x; r.sy = q0.y;
+    r.sxx = (float)__hiloint2double(__float_as_int(q0.w), __float_as_int(q0.z));
+    r.sxy = (float)d1.x; r.syy = (float)d1.y;
+    r.se = q2.x;
+    r.flags = __float_as_uint(q2.y);
     r.f[0] = q3.x; r.f[1] = q3.y; r.f[2] = q3.z; r.f[3] = q3.w;
     r.f[4] = r.f[5] = r.f[6] = r.f[7] = 0.f;
     if (channels > 5) {
