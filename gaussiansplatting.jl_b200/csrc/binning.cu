@@ -631,6 +631,52 @@ tile_ranges32_kernel(const int64_t m, const uint32_t *__restrict__ tiles, uint32
     }
 }
 
+// Tiles by falling instance count: a counting sort on 4 log2(count + 1) (64 buckets, 19 % resolution) by ONE CTA — a few
+// thousand tiles.  The compositing kernels take their tiles in this order: CTAs are dispatched in launch order, so the
+// grid ends on its shortest tiles instead of whatever the raster order leaves for last (the tail cost 3-5 % of both
+// kernels on the uniform synthetic scenes; on real, clustered scenes the heaviest tile can be 10x the median).
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(const int n_tiles, const uint2 *__restrict__ ranges, uint32_t *__restrict__ order) {
+    __shared__ uint32_t s_cnt[64], s_base[64];
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    auto bucket = [](uint2 r) {
+        const int b = (int)(4.0f * __log2f((float)(r.y - r.x) + 1.0f));
+        return 63 - (b > 63 ? 63 : b);  // heaviest first
+    };
+    // neighbouring tiles carry similar loads: a warp's 32 tiles fall into a few buckets, so the shared-memory atomics are
+    // aggregated per bucket with MATCH.ANY (32-way conflicts on 64 counters otherwise)
+    const int lane = threadIdx.x & 31;
+    const int n_round = (n_tiles + (int)blockDim.x - 1) / (int)blockDim.x * (int)blockDim.x;  // warp-uniform trip count
+    for (int t = threadIdx.x; t < n_round; t += blockDim.x) {
+        const int b = t < n_tiles ? bucket(ranges[t]) : 64 + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        if (t < n_tiles && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[b], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // exclusive scan of the 64 counters by one warp
+        const uint32_t c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
+        uint32_t incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        s_base[2 * lane] = incl - c0 - c1;
+        s_base[2 * lane + 1] = incl - c1;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_round; t += blockDim.x) {
+        const int b = t < n_tiles ? bucket(ranges[t]) : 64 + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (t < n_tiles && lane == leader) base = atomicAdd(&s_base[b], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (t < n_tiles) order[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)t;
+    }
+}
+
 // the canonical sorted keys (tile << 32 | bits(depth)) from the sorted tile ids and Gaussian ids
 __global__ void __launch_bounds__(256)
 materialize_keys_kernel(const int64_t m, const uint32_t *__restrict__ tiles, const uint32_t *__restrict__ vals,
@@ -808,7 +854,12 @@ void launch_duplicate_tiles(const DevCamera &cam, int64_t n, const GeomPtrs &g, 
                             uint32_t *tiles, uint32_t *vals, const SortPlan &plan, uint32_t *ghist, cudaStream_t s) {
     if (n <= 0) return;
     int64_t blocks = (n + DUPC_THREADS - 1) / DUPC_THREADS;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        const char *e = getenv("GSR_DUP_CTAS_PER_SM");
+        per_sm = (e && atoi(e) > 0) ? atoi(e) : 4;
+    }
+    if (blocks > 148 * per_sm) blocks = 148 * per_sm;
     duplicate_coop_kernel<<<(unsigned)blocks, DUPC_THREADS, 0, s>>>(n, cam.grid_x, cam.grid_y, g.radii, g.means2d, offsets,
                                                                   perm, tiles, vals, plan.passes, ghist);
     count_launch();
@@ -851,6 +902,12 @@ void launch_sort_tiles(const SortPlan &plan, int64_t m, const uint32_t *tiles_in
 void launch_tile_ranges32(int64_t m, const uint32_t *tiles_sorted, uint32_t *ranges, cudaStream_t s) {
     if (m <= 0) return;
     tile_ranges32_kernel<<<(unsigned)((m + 1023) / 1024), 256, 0, s>>>(m, tiles_sorted, ranges);
+    count_launch();
+}
+
+void launch_tile_order(int64_t n_tiles, const uint32_t *ranges, uint32_t *order, cudaStream_t s) {
+    if (n_tiles <= 0) return;
+    tile_order_kernel<<<1, 1024, 0, s>>>((int)n_tiles, reinterpret_cast<const uint2 *>(ranges), order);
     count_launch();
 }
 

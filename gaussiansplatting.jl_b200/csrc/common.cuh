@@ -133,15 +133,18 @@ void launch_duplicate_tiles(const DevCamera &cam, int64_t n, const GeomPtrs &g, 
 void launch_sort_tiles(const SortPlan &plan, int64_t m, const uint32_t *tiles_in, const uint32_t *vals_in, uint32_t *tiles_out,
                        uint32_t *vals_out, uint32_t *tiles_tmp, uint32_t *vals_tmp, uint32_t *temp_words, cudaStream_t s);
 void launch_tile_ranges32(int64_t m, const uint32_t *tiles_sorted, uint32_t *ranges, cudaStream_t s);
+// order[0..n_tiles): the tiles sorted by falling instance count (19 % resolution), for the compositing kernels' CTA order
+void launch_tile_order(int64_t n_tiles, const uint32_t *ranges, uint32_t *order, cudaStream_t s);
 void launch_materialize_keys(int64_t m, const uint32_t *tiles_sorted, const uint32_t *vals_sorted, const float *depths,
                              uint64_t *keys_sorted, cudaStream_t s);
 
 // both return 0, or -1 when no kernel was compiled for `math_mode`
-int launch_render_forward(int channels, int math_mode, int width, int height, const uint32_t *ranges,
+// order: tile ids in the order the CTAs should take them (launch_tile_order), or nullptr for raster order
+int launch_render_forward(int channels, int math_mode, int width, int height, const uint32_t *ranges, const uint32_t *order,
                           const uint32_t *vals_sorted, const float4 *rec, const float *bg, float *image,
                           uint32_t *n_contrib, float *accum_alpha, uint8_t *covis, float *uncert, cudaStream_t s);
 
-int launch_render_backward(int channels, int math_mode, int width, int height, const uint32_t *ranges,
+int launch_render_backward(int channels, int math_mode, int width, int height, const uint32_t *ranges, const uint32_t *order,
                            const uint32_t *vals_sorted, const float4 *rec, const float *bg, const float *vpixels,
                            const uint32_t *n_contrib, const float *accum_alpha, float *gacc, cudaStream_t s);
 int render_math_mode_supported(int math_mode);

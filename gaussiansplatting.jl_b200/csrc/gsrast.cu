@@ -52,6 +52,8 @@ struct GsrHandle {
     size_t sort_temp_cap = 0;  // words
     // ImageState
     uint32_t *ranges = nullptr, *n_contrib = nullptr;
+    uint32_t *tile_order = nullptr;  // tiles by falling instance count (CTA order of the compositing kernels)
+    bool use_tile_order = false;     // GSR_TILE_ORDER=1: heaviest tiles first (pays on clustered scenes)
     float *accum_alpha = nullptr;
     // depth pre-sort of the Gaussians (binning.cu): ping-pong pairs, the permutation, tiles touched scanned in that order
     bool presort = true;               // GSR_PRESORT=0 restores the single 5-pass instance sort (A/B measurements)
@@ -333,6 +335,10 @@ int gsr_create(const GsrConfig *cfg, GsrHandle **out) {
     h->pplan = presort_plan(h->plan);
     h->tplan = tile_only_plan(h->plan);
     {
+        const char *e = getenv("GSR_TILE_ORDER");
+        h->use_tile_order = e && atoi(e) != 0;
+    }
+    {
         const char *e = getenv("GSR_PRESORT");
         // (the cooperative duplicate packs a rectangle's origin and width into 10 + 12 + 10 bits)
         h->presort = !(e && atoi(e) == 0) && h->grid_x <= 1023 && h->grid_y <= 4095;
@@ -341,6 +347,7 @@ int gsr_create(const GsrConfig *cfg, GsrHandle **out) {
     int rc = GSR_OK;
     do {
         if ((e = dev_alloc(h, &h->ranges, 2 * (size_t)h->n_tiles)) != cudaSuccess) break;
+        if ((e = dev_alloc(h, &h->tile_order, (size_t)h->n_tiles)) != cudaSuccess) break;
         if ((e = dev_alloc(h, &h->n_contrib, px)) != cudaSuccess) break;
         if ((e = dev_alloc(h, &h->accum_alpha, px)) != cudaSuccess) break;
         if ((e = cudaHostAlloc(reinterpret_cast<void **>(&h->total_host), sizeof(int64_t), cudaHostAllocMapped)) != cudaSuccess) break;
@@ -382,6 +389,7 @@ int gsr_destroy(GsrHandle *h) {
     gsr_release_scene_buffers(h);
     const size_t px = (size_t)h->cfg.width * h->cfg.height;
     dev_free(h, h->ranges, 2 * (size_t)h->n_tiles);
+    dev_free(h, h->tile_order, (size_t)h->n_tiles);
     dev_free(h, h->n_contrib, px);
     dev_free(h, h->accum_alpha, px);
     dev_free(h, h->loss_maps, 9 * px);
@@ -540,6 +548,7 @@ static int forward_impl(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t s
             StageTimer tm(h, s, GSR_STAGE_RANGES);
             CK(cudaMemsetAsync(h->ranges, 0, 2 * (size_t)h->n_tiles * sizeof(uint32_t), s));  // rasterizer.jl:375
             launch_tile_ranges32(m, t_out, h->ranges, s);
+            if (h->use_tile_order) launch_tile_order(h->n_tiles, h->ranges, h->tile_order, s);
         }
     } else {
         {
@@ -556,12 +565,14 @@ static int forward_impl(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t s
             StageTimer tm(h, s, GSR_STAGE_RANGES);
             CK(cudaMemsetAsync(h->ranges, 0, 2 * (size_t)h->n_tiles * sizeof(uint32_t), s));  // rasterizer.jl:375
             launch_tile_ranges(m, h->keys_sorted, h->ranges, s);
+            if (h->use_tile_order) launch_tile_order(h->n_tiles, h->ranges, h->tile_order, s);
         }
     }
+    const uint32_t *order = h->use_tile_order ? h->tile_order : nullptr;
     {
         StageTimer tm(h, s, GSR_STAGE_RENDER_FWD);
         float bg[8] = {background[0], background[1], background[2], 0.f, 0.f, 0.f, 0.f, 0.f};  // rasterizer.jl:411-414
-        if (launch_render_forward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,
+        if (launch_render_forward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, order, h->vals_sorted, h->g.rec,
                                   bg, image_out, h->n_contrib, h->accum_alpha, covis, uncert, s))
             return fail(h, GSR_EINVAL, "no compositing kernel for this math_mode");
     }
@@ -634,7 +645,8 @@ static int backward_impl(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t 
     if (h->last_m > 0) {
         StageTimer tm(h, s, GSR_STAGE_RENDER_BWD);
         float bg[8] = {background[0], background[1], background[2], 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (launch_render_backward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,
+        if (launch_render_backward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges,
+                                   h->use_tile_order ? h->tile_order : nullptr, h->vals_sorted, h->g.rec,
                                    bg, vpixels, h->n_contrib, h->accum_alpha, h->g.gacc, s))
             return fail(h, GSR_EINVAL, "no compositing kernel for this math_mode");
     }
@@ -704,7 +716,8 @@ int gsr_backward_render(GsrHandle *h, int64_t n, const float background[3], cons
     if (h->last_m > 0) {
         StageTimer tm(h, s, GSR_STAGE_RENDER_BWD);
         float bg[8] = {background[0], background[1], background[2], 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (launch_render_backward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges, h->vals_sorted, h->g.rec,
+        if (launch_render_backward(ch, h->cfg.math_mode, h->cfg.width, h->cfg.height, h->ranges,
+                                   h->use_tile_order ? h->tile_order : nullptr, h->vals_sorted, h->g.rec,
                                    bg, vpixels, h->n_contrib, h->accum_alpha, h->g.gacc, s))
             return fail(h, GSR_EINVAL, "no compositing kernel for this math_mode");
     }
