@@ -349,6 +349,15 @@ GSR_API int gsr_measure_fp32_peak(double *tflops, void *stream);
 GSR_API int gsr_debug_exp_neg(const float *sigma_dev, float *split_dev, float *libdevice_dev, float *inlined_dev, int64_t n,
                               void *stream);
 
+/* Environment knobs, read once (per handle / per process).  Measurement aids, not part of the supported surface; every
+ * setting produces the same results bit for bit.
+ *   GSR_PRESORT=0          one 5-pass radix sort of the 64-bit instance keys instead of the depth pre-sort of the Gaussians +
+ *                          the tile-digit sort of 32-bit instance keys (default 1)
+ *   GSR_TILE_ORDER=1       the compositing kernels take their tiles heaviest first (default 0: raster order)
+ *   GSR_SORT_IPT=8|16, GSR_PRESORT_IPT=8|16    keys per thread of the radix passes over the instances / the Gaussians
+ *   GSR_SORT_RANK=match|ballot|auto            ranking primitive of the radix passes
+ *   GSR_DUP_CTAS_PER_SM=n  CTAs per SM of the cooperative duplicate kernel (default 4) */
+
 /* Kernels launched by this library since process start (bench.py's gpu_launches). */
 GSR_API int64_t gsr_launch_count(void);
 
