@@ -98,11 +98,15 @@ class ViewBatchBackward:
     `gsr_backward` calls: the parameters are read once and the gradient table is written once instead of V
     read-modify-write passes.  Result == sum over the V views of ∇rasterize, same layout as `GradientTable`."""
 
-    def __init__(self, rast, n: int, K: int, cameras: list, group=None, scatter_only: bool = False):
+    def __init__(self, rast, n: int, K: int, cameras: list, group=None, scatter_only: bool = False,
+                 stage_accumulators: bool | None = None):
         """scatter_only: every rank ends with the reduced rows of its own Gaussian slice `slice_rows()` only (reduce-
-        scatter semantics, for a Gaussian-sharded optimizer) instead of the full replicated table (all-reduce)."""
+        scatter semantics, for a Gaussian-sharded optimizer) instead of the full replicated table (all-reduce).
+        stage_accumulators: the compositing backward accumulates into ordinary device memory and the finished accumulator
+        is copied into the peer-mapped buffer (default: on when there are several ranks, GSR_STAGE_ACC=0/1 overrides)."""
         self.rast, self.n, self.K, self.cameras = rast, n, K, list(cameras)
         self.scatter_only = bool(scatter_only)
+        self._stage_opt = stage_accumulators
         self.V = len(self.cameras)
         assert 1 <= self.V <= 16, "1..16 views per batch"
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -128,6 +132,11 @@ class ViewBatchBackward:
             bases, self.table_ptrs = [self.gacc.data_ptr()], [self.table_flat.data_ptr()]
         if self.scatter_only:
             self.table_ptrs = [p if r == self.rank else 0 for r, p in enumerate(self.table_ptrs)]
+        import os
+        env = os.environ.get("GSR_STAGE_ACC")
+        self.stage = multi and (self._stage_opt if self._stage_opt is not None else (env != "0" if env is not None else True))
+        self.private_acc = ([torch.empty(n * self.af, dtype=torch.float32, device=dev) for _ in range(slots)]
+                            if self.stage else None)
         stride = n * self.af * 4
         self.view_ptrs = [bases[view_owner(v, self.world)[0]] + view_owner(v, self.world)[1] * stride for v in range(self.V)]
         self.local_acc = [self.gacc[j * n * self.af:(j + 1) * n * self.af] for j in range(slots)]
@@ -149,12 +158,14 @@ class ViewBatchBackward:
         """`vpixels[v]` = cotangent of view v (needed for this rank's views only).  Returns the table views."""
         r = self.rast
         for j, v in enumerate(self.mine):
-            r.set_accumulator(self.local_acc[j])  # pointer swap: this view's accumulator
+            r.set_accumulator(self.private_acc[j] if self.stage else self.local_acc[j])  # pointer swap
             img = r._forward(params["means"], params["shs"], params["opac"], params["scales"], params["rots"], None, None,
                              self.cameras[v], sh_degree, background, None, None)
             if images is not None:
                 images[v] = img.clone()
             r.backward_render(vpixels[v], self.n, background)
+            if self.stage:  # the peers read the finished accumulator from the peer-mapped copy
+                self.local_acc[j].copy_(self.private_acc[j], non_blocking=True)
         if self.h_gacc is not None:
             self.h_gacc.barrier(channel=0)   # every rank's accumulators are complete
         r.backward_gaussians_views(self.cameras, self.view_ptrs, self.world, self.rank, self.table_ptrs, params["means"],
