@@ -40,6 +40,23 @@ pack_flags_kernel(const int64_t n, const int AF, const int32_t *__restrict__ rad
     gacc[i * (int64_t)AF + GSR_ACC_FLAGS_SLOT] = __uint_as_float(f);
 }
 
+// accumulator rows -> exchange rows (common.cuh): one thread per Gaussian, coalesced enough for a 100-MB one-off pass
+__global__ void __launch_bounds__(256)
+export_rows_kernel(const int64_t n, const int channels, const float *__restrict__ gacc, float *__restrict__ rows) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const AccRow a = load_acc_row(gacc + i * (int64_t)acc_floats(channels), channels);
+    float4 *dst = reinterpret_cast<float4 *>(rows + i * (int64_t)exchange_floats(channels));
+    dst[0] = make_float4(a.sx, a.sy, a.sxx, a.sxy);
+    dst[1] = make_float4(a.syy, a.se, a.f[0], a.f[1]);
+    if (channels > 5) {
+        dst[2] = make_float4(a.f[2], a.f[3], 0.f, 0.f);
+        dst[3] = make_float4(a.f[5], a.f[6], a.f[7], __uint_as_float(a.flags));
+    } else {
+        dst[2] = make_float4(a.f[2], a.f[3], 0.f, __uint_as_float(a.flags));
+    }
+}
+
 // rast.gstate.∇means_2d of the LOCAL view for all Gaussians (strategy.jl:85-86 reads it): conic * (Sx, Sy)
 __global__ void __launch_bounds__(256)
 grad_means2d_kernel(const int64_t n, const int AF, const int32_t *__restrict__ radii, const float *__restrict__ conics,
@@ -108,7 +125,8 @@ backward_gaussians_peers_kernel(const PeerArgs A) {
 
         for (int v = 0; v < A.n_views; v++) {
             // ---- this view's accumulator row, straight from the memory of the rank that rendered it (P2P load) ----
-            const AccRow a = load_acc_row(A.gacc[v] + i * (int64_t)AF, A.channels);
+            const AccRow a = A.exchange_rows ? load_exchange_row(A.gacc[v] + i * (int64_t)exchange_floats(A.channels), A.channels)
+                                             : load_acc_row(A.gacc[v] + i * (int64_t)AF, A.channels);
             const uint32_t flags = a.flags;
             if (!(flags & 8u)) continue;  // culled in view v (projection.jl:172-176)
             const PeerCamera &cam = A.cams[v];
@@ -222,6 +240,12 @@ backward_gaussians_peers_kernel(const PeerArgs A) {
 void launch_pack_flags(int64_t n, int channels, const int32_t *radii, const uint8_t *clamped, float *gacc, cudaStream_t s) {
     if (n <= 0) return;
     pack_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, acc_floats(channels), radii, clamped, gacc);
+    count_launch();
+}
+
+void launch_export_rows(int64_t n, int channels, const float *gacc, float *rows, cudaStream_t s) {
+    if (n <= 0) return;
+    export_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, channels, gacc, rows);
     count_launch();
 }
 

@@ -46,6 +46,30 @@ struct AccRow {
     uint32_t flags;
     float f[8];  // per-channel feature cotangents; f[4] (the constant-1 alpha feature) is always 0
 };
+// EXCHANGE form of an accumulator row — what crosses NVLink in the fused multi-GPU backward: the same quantities as plain
+// floats, 12 (channels <= 6) / 16 floats per row:  {Sx, Sy, Sxx, Sxy, Syy, Se, f0, f1, f2, f3, -, flags | f5, f6, f7, -}
+// (flags in the last slot of the row).  The per-Gaussian chain converts the fp64 sums to fp32 anyway, so nothing is
+// lost; the rows are a quarter smaller and the peers pull them with 3 instead of 4 128-bit loads per view and Gaussian
+// (those remote loads set the fused kernel's time at 8 ranks: 0.56 ms with 64-byte rows against 0.38 ms with 48-byte ones).
+__host__ __device__ constexpr int exchange_floats(int channels) { return channels <= 6 ? 12 : 16; }
+__device__ __forceinline__ AccRow load_exchange_row(const float *row, const int channels) {
+    AccRow r;
+    const float4 a0 = *reinterpret_cast<const float4 *>(row);
+    const float4 a1 = *reinterpret_cast<const float4 *>(row + 4);
+    const float4 a2 = *reinterpret_cast<const float4 *>(row + 8);
+    r.sx = a0.x; r.sy = a0.y; r.sxx = a0.z; r.sxy = a0.w; r.syy = a1.x; r.se = a1.y;
+    r.f[0] = a1.z; r.f[1] = a1.w; r.f[2] = a2.x; r.f[3] = a2.y;
+    r.f[4] = r.f[5] = r.f[6] = r.f[7] = 0.f;
+    r.flags = __float_as_uint(a2.w);
+    if (channels > 5) {
+        const float4 a3 = *reinterpret_cast<const float4 *>(row + 12);
+        r.f[5] = a3.x; r.f[6] = a3.y; r.f[7] = a3.z;
+        r.flags = __float_as_uint(a3.w);
+    }
+    if (channels == 3) r.f[3] = 0.f;
+    return r;
+}
+
 __device__ __forceinline__ AccRow load_acc_row(const float *acc, const int channels) {
     AccRow r;
     const float4 q0 = *reinterpret_cast<const float4 *>(acc);       // 128-bit loads (rows are 16-byte aligned)
@@ -175,12 +199,15 @@ struct PeerArgs {
     const float *gacc[GSR_MAX_VIEWS];  // that view's accumulator [n][AF], in the memory of the rank that rendered it
     float *table[GSR_MAX_PEERS];       // every rank's gradient table: [vrot 4n | vmeans 3n | vscales 3n | vopac n | vshs 3Kn]
     int32_t n_views, world, rank;
+    int32_t exchange_rows;  // 1: gacc[v] holds EXCHANGE rows (exchange_floats per row), 0: the handle's own accumulator layout
     int64_t n, lo, hi;
     int32_t sh_degree, K, channels, sh_stride;
     int32_t vsh_aligned;  // every table's SH segment (offset 11n floats) is 16-byte aligned
     const float *means, *shs, *opac, *scales, *rots;
 };
 void launch_pack_flags(int64_t n, int channels, const int32_t *radii, const uint8_t *clamped, float *gacc, cudaStream_t s);
+// accumulator rows (+ visibility / clamp flags) -> exchange rows
+void launch_export_rows(int64_t n, int channels, const float *gacc, float *rows, cudaStream_t s);
 void launch_grad_means2d(int64_t n, int channels, const int32_t *radii, const float *conics, const float *gacc,
                          float2 *out, cudaStream_t s);
 int launch_backward_gaussians_peers(const PeerArgs &args, cudaStream_t s);

@@ -726,8 +726,18 @@ int gsr_backward_render(GsrHandle *h, int64_t n, const float background[3], cons
     return GSR_OK;
 }
 
+int gsr_export_accumulator(GsrHandle *h, int64_t n, float *rows_dev, void *stream) {
+    if (!h) return GSR_EINVAL;
+    if (!rows_dev || (reinterpret_cast<uintptr_t>(rows_dev) & 15))
+        return fail(h, GSR_EINVAL, "gsr_export_accumulator: need a 16-byte aligned destination");
+    if (!h->fwd_valid || n != h->last_n) return fail(h, GSR_ESTATE, "gsr_export_accumulator: no matching gsr_forward / gsr_backward_render");
+    launch_export_rows(n, h->cfg.channels, h->g.gacc, rows_dev, static_cast<cudaStream_t>(stream));
+    CK(cudaGetLastError());
+    return GSR_OK;
+}
+
 int gsr_backward_gaussians_views(GsrHandle *h, int32_t n_views, const GsrCamera *cams, const float *const *view_gacc,
-                                 int32_t world, int32_t rank, float *const *peer_tables, int64_t n, int32_t sh_degree,
+                                 int32_t exchange_rows, int32_t world, int32_t rank, float *const *peer_tables, int64_t n, int32_t sh_degree,
                                  int32_t K, const float *means, const float *shs, const float *opacities,
                                  const float *scales, const float *rotations, void *stream) {
     if (!h) return GSR_EINVAL;
@@ -766,6 +776,7 @@ int gsr_backward_gaussians_views(GsrHandle *h, int32_t n_views, const GsrCamera 
         if (reinterpret_cast<uintptr_t>(peer_tables[p] + 11 * n) & 15) a.vsh_aligned = 0;
     }
     a.n_views = n_views;
+    a.exchange_rows = exchange_rows ? 1 : 0;
     a.world = world;
     a.rank = rank;
     a.n = n;
@@ -788,8 +799,8 @@ int gsr_backward_gaussians_peers(GsrHandle *h, int32_t world, int32_t rank, cons
                                  const float *const *peer_gacc, float *const *peer_tables, int64_t n, int32_t sh_degree,
                                  int32_t K, const float *means, const float *shs, const float *opacities,
                                  const float *scales, const float *rotations, void *stream) {
-    // one view per rank: view v's accumulator is rank v's
-    return gsr_backward_gaussians_views(h, world, cams, peer_gacc, world, rank, peer_tables, n, sh_degree, K, means, shs,
+    // one view per rank: view v's accumulator is rank v's, in the handle's own row layout
+    return gsr_backward_gaussians_views(h, world, cams, peer_gacc, 0, world, rank, peer_tables, n, sh_degree, K, means, shs,
                                         opacities, scales, rotations, stream);
 }
 

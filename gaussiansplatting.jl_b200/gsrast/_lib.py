@@ -40,7 +40,7 @@ EXPORTS = ["gsr_version", "gsr_last_error", "gsr_create", "gsr_destroy", "gsr_re
            "gsr_forward_backward_host", "gsr_identify_tile_range", "gsr_sort_pairs", "gsr_launch_count",
            "gsr_profile_enable", "gsr_profile_get", "gsr_measure_fp32_peak", "gsr_debug_exp_neg", "gsr_forward_backward_host_async",
            "gsr_host_wait", "gsr_host_timeline", "gsr_set_accumulator", "gsr_backward_render",
-           "gsr_backward_gaussians_peers", "gsr_backward_gaussians_views", "gsr_ssim_forward", "gsr_ssim_backward", "gsr_photometric_loss", "gsr_forward_raw", "gsr_backward_raw", "gsr_ply_open", "gsr_ply_read",
+           "gsr_backward_gaussians_peers", "gsr_backward_gaussians_views", "gsr_export_accumulator", "gsr_ssim_forward", "gsr_ssim_backward", "gsr_photometric_loss", "gsr_forward_raw", "gsr_backward_raw", "gsr_ply_open", "gsr_ply_read",
            "gsr_ply_close", "gsr_ply_write", "gsr_ply_write_scales", "gsr_ply_last_error", "gsr_densify_masks", "gsr_prune_mask",
            "gsr_mask_offsets_scratch_words", "gsr_mask_offsets", "gsr_gather_rows", "gsr_split_children"]
 STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "render_fwd", "zero_grads", "render_bwd", "gauss_bwd",
@@ -113,8 +113,9 @@ def load() -> C.CDLL:
     lib.gsr_backward_render.argtypes = [vp, i64, C.POINTER(C.c_float), vp, vp]
     lib.gsr_backward_gaussians_peers.argtypes = [vp, i32, i32, C.POINTER(GsrCamera), C.POINTER(vp), C.POINTER(vp), i64, i32,
                                                  i32, vp, vp, vp, vp, vp, vp]
-    lib.gsr_backward_gaussians_views.argtypes = [vp, i32, C.POINTER(GsrCamera), C.POINTER(vp), i32, i32, C.POINTER(vp), i64,
-                                                 i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.gsr_backward_gaussians_views.argtypes = [vp, i32, C.POINTER(GsrCamera), C.POINTER(vp), i32, i32, i32, C.POINTER(vp),
+                                                 i64, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.gsr_export_accumulator.argtypes = [vp, i64, vp, vp]
     lib.gsr_ssim_forward.argtypes = [i32, i32, i32, i32, vp, vp, C.c_float, C.c_float, i32, vp, vp, vp, vp, vp]
     lib.gsr_ssim_backward.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.gsr_photometric_loss.argtypes = [vp, vp, vp, C.c_float, vp, vp, vp]

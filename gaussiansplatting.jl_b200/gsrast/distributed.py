@@ -91,55 +91,52 @@ class ViewBatchBackward:
     """A batch of V views (V <= 16) sharded round-robin over the ranks — several views per rank, or all of them on one
     GPU — with ONE fused per-Gaussian backward + exchange per batch (csrc/backward_peers.cu, gsr_backward_gaussians_views).
 
-    Every view gets its own moment accumulator (64 / 80 B per Gaussian).  After this rank's forwards and compositing
-    backwards, rank r reduces ITS slice of the Gaussians over all V accumulators — loading the other ranks' rows over
-    NVLink — and stores the finished rows into every rank's table: compute + reduce-scatter + all-gather in one kernel,
-    once per batch.  On a single GPU (world == 1, no process group needed) the same kernel replaces V accumulating
-    `gsr_backward` calls: the parameters are read once and the gradient table is written once instead of V
-    read-modify-write passes.  Result == sum over the V views of ∇rasterize, same layout as `GradientTable`."""
+    Every view gets its own moment accumulator (64 / 80 B per Gaussian, second moments in fp64).  After this rank's forwards
+    and compositing backwards, rank r reduces ITS slice of the Gaussians over all V views and stores the finished rows into
+    every rank's table: compute + reduce-scatter + all-gather in one kernel, once per batch.  Across GPUs the accumulators
+    are published as fp32 EXCHANGE rows (48 / 64 B, gsr_export_accumulator) in symmetric memory, which the owner of a
+    slice loads over NVLink.  On a single GPU (world == 1, no process group needed) the same kernel reads the accumulators
+    directly and replaces V accumulating `gsr_backward` calls: the parameters are read once and the gradient table is
+    written once instead of V read-modify-write passes.  Result == sum over the V views of ∇rasterize, same layout as
+    `GradientTable`."""
 
-    def __init__(self, rast, n: int, K: int, cameras: list, group=None, scatter_only: bool = False,
-                 stage_accumulators: bool | None = None):
+    def __init__(self, rast, n: int, K: int, cameras: list, group=None, scatter_only: bool = False):
         """scatter_only: every rank ends with the reduced rows of its own Gaussian slice `slice_rows()` only (reduce-
-        scatter semantics, for a Gaussian-sharded optimizer) instead of the full replicated table (all-reduce).
-        stage_accumulators: the compositing backward accumulates into ordinary device memory and the finished accumulator
-        is copied into the peer-mapped buffer (default: on when there are several ranks, GSR_STAGE_ACC=0/1 overrides)."""
+        scatter semantics, for a Gaussian-sharded optimizer) instead of the full replicated table (all-reduce)."""
         self.rast, self.n, self.K, self.cameras = rast, n, K, list(cameras)
         self.scatter_only = bool(scatter_only)
-        self._stage_opt = stage_accumulators
         self.V = len(self.cameras)
         assert 1 <= self.V <= 16, "1..16 views per batch"
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.multi = multi
         self.group = (group if group is not None else dist.group.WORLD) if multi else None
         self.world = dist.get_world_size(self.group) if multi else 1
         self.rank = dist.get_rank(self.group) if multi else 0
         self.mine = views_for_rank(self.V, self.rank, self.world)
-        self.af = 16 if rast.channels <= 6 else 20  # csrc/common.cuh acc_floats
+        self.af = 16 if rast.channels <= 6 else 20   # csrc/common.cuh acc_floats: the handle's accumulator rows
+        self.ef = 12 if rast.channels <= 6 else 16   # csrc/common.cuh exchange_floats: what crosses NVLink
         dev = rast.device
-        slots = (self.V + self.world - 1) // self.world  # accumulators per rank (same on every rank: symmetric)
+        slots = (self.V + self.world - 1) // self.world  # views per rank (same on every rank: symmetric)
         per = 4 + 3 + 3 + 1 + 3 * K
+        self.acc = [torch.empty(n * self.af, dtype=torch.float32, device=dev) for _ in range(slots)]
         if multi:
             import torch.distributed._symmetric_memory as symm_mem
-            self.gacc = symm_mem.empty(slots * n * self.af, dtype=torch.float32, device=dev)
-            self.h_gacc = symm_mem.rendezvous(self.gacc, self.group)
+            self.rows = symm_mem.empty(slots * n * self.ef, dtype=torch.float32, device=dev)
+            self.h_gacc = symm_mem.rendezvous(self.rows, self.group)
             self.table_flat = symm_mem.empty(n * per, dtype=torch.float32, device=dev)
             self.h_table = symm_mem.rendezvous(self.table_flat, self.group)
             bases, self.table_ptrs = list(self.h_gacc.buffer_ptrs), list(self.h_table.buffer_ptrs)
+            stride = n * self.ef * 4
+            self.view_ptrs = [bases[view_owner(v, self.world)[0]] + view_owner(v, self.world)[1] * stride
+                              for v in range(self.V)]
+            self.local_rows = [self.rows[j * n * self.ef:(j + 1) * n * self.ef] for j in range(slots)]
         else:
-            self.gacc = torch.empty(slots * n * self.af, dtype=torch.float32, device=dev)
             self.table_flat = torch.empty(n * per, dtype=torch.float32, device=dev)
             self.h_gacc = self.h_table = None
-            bases, self.table_ptrs = [self.gacc.data_ptr()], [self.table_flat.data_ptr()]
+            self.table_ptrs = [self.table_flat.data_ptr()]
+            self.view_ptrs = [self.acc[v].data_ptr() for v in range(self.V)]
         if self.scatter_only:
             self.table_ptrs = [p if r == self.rank else 0 for r, p in enumerate(self.table_ptrs)]
-        import os
-        env = os.environ.get("GSR_STAGE_ACC")
-        self.stage = multi and (self._stage_opt if self._stage_opt is not None else (env != "0" if env is not None else True))
-        self.private_acc = ([torch.empty(n * self.af, dtype=torch.float32, device=dev) for _ in range(slots)]
-                            if self.stage else None)
-        stride = n * self.af * 4
-        self.view_ptrs = [bases[view_owner(v, self.world)[0]] + view_owner(v, self.world)[1] * stride for v in range(self.V)]
-        self.local_acc = [self.gacc[j * n * self.af:(j + 1) * n * self.af] for j in range(slots)]
         self.views, off = {}, 0
         for name, s_ in SEGMENTS:
             width = 3 * K if s_ is None else s_
@@ -158,20 +155,21 @@ class ViewBatchBackward:
         """`vpixels[v]` = cotangent of view v (needed for this rank's views only).  Returns the table views."""
         r = self.rast
         for j, v in enumerate(self.mine):
-            r.set_accumulator(self.private_acc[j] if self.stage else self.local_acc[j])  # pointer swap
+            r.set_accumulator(self.acc[j])  # pointer swap: this view's accumulator
             img = r._forward(params["means"], params["shs"], params["opac"], params["scales"], params["rots"], None, None,
                              self.cameras[v], sh_degree, background, None, None)
             if images is not None:
                 images[v] = img.clone()
             r.backward_render(vpixels[v], self.n, background)
-            if self.stage:  # the peers read the finished accumulator from the peer-mapped copy
-                self.local_acc[j].copy_(self.private_acc[j], non_blocking=True)
+            if self.multi:  # publish the finished accumulator as fp32 exchange rows in peer-mapped memory
+                r.export_accumulator(self.n, self.local_rows[j])
         if self.h_gacc is not None:
-            self.h_gacc.barrier(channel=0)   # every rank's accumulators are complete
+            self.h_gacc.barrier(channel=0)   # every rank's rows are complete
         r.backward_gaussians_views(self.cameras, self.view_ptrs, self.world, self.rank, self.table_ptrs, params["means"],
-                                   params["shs"], params["opac"], params["scales"], params["rots"], sh_degree)
+                                   params["shs"], params["opac"], params["scales"], params["rots"], sh_degree,
+                                   exchange_rows=self.multi)
         if self.h_table is not None:
-            self.h_table.barrier(channel=0)  # every rank's table is complete (and nobody still reads my accumulators)
+            self.h_table.barrier(channel=0)  # every rank's table is complete (and nobody still reads my rows)
         return self.views
 
 

@@ -316,8 +316,14 @@ class GaussianRasterizer:
             check(_lib.lib().gsr_backward_gaussians_peers(self._h, world, rank, cams, ga, tb, n, sh_degree, K, _ptr(means),
                                                           _ptr(shs), _ptr(opac), _ptr(scales), _ptr(rots), stream), self._h)
 
+    def export_accumulator(self, n: int, rows: torch.Tensor):
+        """gsr_export_accumulator: the accumulator of the last backward_render as exchange rows ([n][12 or 16] floats)."""
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().gsr_export_accumulator(self._h, n, _ptr(rows), stream), self._h)
+
     def backward_gaussians_views(self, cameras, view_gacc_ptrs, world, rank, table_ptrs, means, shs, opac, scales, rots,
-                                 sh_degree):
+                                 sh_degree, exchange_rows: bool = False):
         """gsr_backward_gaussians_views: per-Gaussian backward of a whole view batch (one accumulator per view, wherever
         it was rendered), reduced over the views and stored into every rank's table."""
         n, K = means.shape[0], shs.shape[1]
@@ -327,7 +333,8 @@ class GaussianRasterizer:
         tb = (C.c_void_p * world)(*[(int(p) or None) for p in table_ptrs])  # 0 -> NULL: that rank receives nothing
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         with torch.cuda.device(self.device):
-            check(_lib.lib().gsr_backward_gaussians_views(self._h, nv, cams, ga, world, rank, tb, n, sh_degree, K,
+            check(_lib.lib().gsr_backward_gaussians_views(self._h, nv, cams, ga, int(bool(exchange_rows)), world, rank, tb, n,
+                                                          sh_degree, K,
                                                           _ptr(means), _ptr(shs), _ptr(opac), _ptr(scales), _ptr(rots),
                                                           stream), self._h)
 

@@ -178,10 +178,15 @@ GSR_API int gsr_backward_gaussians_peers(GsrHandle *h, int32_t world, int32_t ra
  * over all n_views and stores the rows into the `world` tables.  On one GPU this replaces n_views accumulating
  * gsr_backward calls — one pass over the parameters and ONE write of the gradient table per batch instead of n_views
  * read-modify-write passes.  gsr_backward_gaussians_peers(world, ...) == this with n_views = world.
+ * exchange_rows != 0: view_gacc[v] holds EXCHANGE rows written by gsr_export_accumulator ([n][12 or 16] plain floats) —
+ * the form to put in peer-mapped memory: a quarter smaller than the handle's own rows (whose second moments are doubles),
+ * and the peers' remote loads of these rows are what bounds the kernel at 8 ranks.  0: the handle's own accumulator layout.
  * peer_tables[p] == NULL for p != rank: rank p does not receive this rank's rows — with only its own pointer set, every
  * rank ends with the reduced rows of ITS slice only (reduce-scatter; a Gaussian-sharded optimizer needs no more). */
+/* After gsr_backward_render: the handle's accumulator (+ the view's visibility / clamp flags) as exchange rows. */
+GSR_API int gsr_export_accumulator(GsrHandle *h, int64_t n, float *rows_dev, void *stream);
 GSR_API int gsr_backward_gaussians_views(GsrHandle *h, int32_t n_views, const GsrCamera *cams, const float *const *view_gacc,
-                                 int32_t world, int32_t rank, float *const *peer_tables, int64_t n, int32_t sh_degree,
+                                 int32_t exchange_rows, int32_t world, int32_t rank, float *const *peer_tables, int64_t n, int32_t sh_degree,
                                  int32_t K, const float *means, const float *shs, const float *opacities,
                                  const float *scales, const float *rotations, void *stream);
 

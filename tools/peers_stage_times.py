@@ -14,9 +14,9 @@ sc = make_config("C2")
 d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in dict(means=sc.means, shs=sc.shs, opac=sc.opacities.reshape(-1, 1), scales=sc.scales, rots=sc.rotations).items()}
 cams = [Camera(fx=sc.fx, fy=sc.fy, width=sc.width, height=sc.height, R=R, t=t) for R, t in (view_pose(v, world, max_yaw_deg=2.0, max_shift=0.1) for v in range(world))]
 vp = torch.from_numpy(make_vpixels(sc.width, sc.height, 5, 1002)).to(dev)
-for stage in (False, True):
+for stage in (True,):
     rast = GaussianRasterizer(width=sc.width, height=sc.height, mode="rgbd", device=dev)
-    f = ViewBatchBackward(rast, sc.n, 16, cams, stage_accumulators=stage)
+    f = ViewBatchBackward(rast, sc.n, 16, cams)
     for _ in range(5): f.step(d, {rank: vp}, 3)
     torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -31,6 +31,6 @@ for stage in (False, True):
         for k, v in rast.stage_times_ms().items(): acc[k] = acc.get(k, 0) + v / 10
     rast.profile(False)
     if rank == 0:
-        print("staged" if stage else "peer-mapped", "accumulators: ms/step", round(float(t), 4), {k: round(v, 4) for k, v in acc.items() if k in ("render_bwd", "gauss_bwd", "zero_grads", "render_fwd")})
+        print("exchange-row accumulators: ms/step", round(float(t), 4), {k: round(v, 4) for k, v in acc.items() if k in ("render_bwd", "gauss_bwd", "zero_grads", "render_fwd")})
     del f, rast
 dist.barrier(); dist.destroy_process_group()
