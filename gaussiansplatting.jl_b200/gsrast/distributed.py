@@ -144,6 +144,19 @@ class ViewBatchBackward:
             self.views[name] = v.view(n, K, 3) if s_ is None else v.view(n, width)
             off += n * width
 
+    def close(self):
+        """Detach the rasterizer from this object's accumulators (it would otherwise keep a pointer into memory that is
+        freed with this object)."""
+        r, self.rast = self.rast, None
+        if r is not None and getattr(r, "_h", None):
+            try:
+                r.set_accumulator(None)
+            except Exception:
+                pass
+
+    def __del__(self):
+        self.close()
+
     def slice_rows(self) -> tuple[int, int]:
         """[lo, hi): the Gaussians whose gradient rows this rank reduces (the kernel's slicing: 64-aligned chunks)."""
         chunk = (self.n + self.world - 1) // self.world
