@@ -158,8 +158,12 @@ GSR_API int gsr_backward(GsrHandle *h, const GsrCamera *cam, int64_t n, int32_t 
 
 /* ---- multi-GPU: per-Gaussian backward fused with the cross-GPU gradient reduction over peer memory -----------
  * (not in the reference, which is single-GPU; semantics = sum over the ranks' views of ∇rasterize)
- * gsr_set_accumulator: make the handle keep its per-Gaussian accumulator ([capacity][16 or 20] floats: 64 B per Gaussian for :rgb / :rgbd, 80 B for :rgbdn) in
- *   caller-provided memory, e.g. a symmetric / peer-mapped allocation (NULL, 0 restores the private buffer).
+ * gsr_set_accumulator: make the handle keep its per-Gaussian accumulator ([capacity][16 or 20] floats: 64 B per
+ *   Gaussian for :rgb / :rgbd, 80 B for :rgbdn; second moments as doubles) in caller-provided memory — one accumulator
+ *   per view of a batch.  A pointer swap when the capacity covers the current scene (the state of the last forward
+ *   stays valid); NULL, 0 restores the private buffer.
+ * gsr_export_accumulator: after gsr_backward_render, the accumulator (+ the view's visibility / clamp flags) as fp32
+ *   EXCHANGE rows ([n][12 or 16] floats) — the form to publish in peer-mapped memory.
  * gsr_backward_render: first half of ∇rasterize — zero-fill + ∇render! into the accumulator (+ ∇means_2d).
  * gsr_backward_gaussians_peers: second half for `world` ranks at once.  Rank `rank` owns the Gaussian slice
  *   [rank*chunk, (rank+1)*chunk): it loads every rank's accumulator rows for that slice (peer_gacc[v], P2P loads),
@@ -183,7 +187,6 @@ GSR_API int gsr_backward_gaussians_peers(GsrHandle *h, int32_t world, int32_t ra
  * and the peers' remote loads of these rows are what bounds the kernel at 8 ranks.  0: the handle's own accumulator layout.
  * peer_tables[p] == NULL for p != rank: rank p does not receive this rank's rows — with only its own pointer set, every
  * rank ends with the reduced rows of ITS slice only (reduce-scatter; a Gaussian-sharded optimizer needs no more). */
-/* After gsr_backward_render: the handle's accumulator (+ the view's visibility / clamp flags) as exchange rows. */
 GSR_API int gsr_export_accumulator(GsrHandle *h, int64_t n, float *rows_dev, void *stream);
 GSR_API int gsr_backward_gaussians_views(GsrHandle *h, int32_t n_views, const GsrCamera *cams, const float *const *view_gacc,
                                  int32_t exchange_rows, int32_t world, int32_t rank, float *const *peer_tables, int64_t n, int32_t sh_degree,
